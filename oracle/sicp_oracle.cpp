@@ -1,0 +1,1108 @@
+// =====================================================================================
+// sicp_oracle.cpp — CPU ORACLE for the Semantic-ICP registration hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load it.  The CUDA library never
+// links, imports or calls anything in this directory.
+//
+// It is a dependency-free restatement (C++17, built with -O3 -ffp-contract=off, optional
+// OpenMP) of the reference's algorithm.  Citations are relative to /root/reference/:
+//   semantic_icp/impl/gicp.hpp:29-175,177-239        GICP::align / computeCovariances
+//   semantic_icp/impl/em_icp.hpp:24-200,202-268,270-344  EM align / getFusedLabels / ComputeCovariances
+//   semantic_icp/impl/semantic_icp.hpp:27-166         SemanticIterativeClosestPoint::align
+//   semantic_icp/impl/semantic_point_cloud.hpp:12-87  addSemanticCloud (per-class kd-tree + covariances)
+//   semantic_icp/pcl_2_semantic.h:14-42               label split, first-appearance order
+//   semantic_icp/gicp_cost_function.h:27-87,98-176    residual, 1x7 Jacobian, Probability (bool!)
+//   semantic_icp/local_parameterization_se3.h:17-36   Plus = T*exp(delta), 7x6 Jacobian
+//   semantic_icp/sqloss.h:13-18                       SQLoss
+//
+// PARITY UNPINNED for the third-party arithmetic: PCL (KdTreeFLANN / transformPointCloud),
+// FLANN, Eigen (JacobiSVD, 3x3 inverse), Sophus (SE3 exp/log/Dx_this_mul_exp_x_at_0) and
+// Ceres (trust-region LM, loss correction) are NOT in /root/reference and not installable
+// here (no network; versions unpinned by the reference's CMakeLists.txt:7-14).  Their
+// published algorithms are restated from the documentation/source as recalled; the reference
+// holds no golden vectors (it has no tests).  What pins this file: the derived known-answer
+// vectors for exec/test_gradient.cc:32-50 (tests/golden/), an independent NumPy transcription
+// of gicp_cost_function.h (tests/golden/make_golden.py), central differences, and OpenCV's
+// FLANN-lineage exact kd-tree as a second opinion for kNN.
+// =====================================================================================
+#include <algorithm>
+#include <cfloat>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <numeric>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+// ------------------------------------------------------------------ 3x3 / vector helpers
+struct M3 { double a[3][3]; };
+struct V3 { double v[3]; };
+
+static inline M3 m3_zero() { M3 r; std::memset(&r, 0, sizeof r); return r; }
+static inline M3 m3_mul(const M3& A, const M3& B) {
+  M3 C;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += A.a[i][k] * B.a[k][j];
+      C.a[i][j] = s;
+    }
+  return C;
+}
+static inline M3 m3_T(const M3& A) {
+  M3 C;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.a[i][j] = A.a[j][i];
+  return C;
+}
+static inline M3 m3_add(const M3& A, const M3& B) {
+  M3 C;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) C.a[i][j] = A.a[i][j] + B.a[i][j];
+  return C;
+}
+static inline V3 m3_v(const M3& A, const V3& x) {
+  V3 y;
+  for (int i = 0; i < 3; i++) y.v[i] = A.a[i][0] * x.v[0] + A.a[i][1] * x.v[1] + A.a[i][2] * x.v[2];
+  return y;
+}
+static inline V3 vT_m3(const V3& x, const M3& A) {  // row vector x^T A
+  V3 y;
+  for (int j = 0; j < 3; j++) y.v[j] = x.v[0] * A.a[0][j] + x.v[1] * A.a[1][j] + x.v[2] * A.a[2][j];
+  return y;
+}
+static inline double dot3(const V3& a, const V3& b) { return a.v[0] * b.v[0] + a.v[1] * b.v[1] + a.v[2] * b.v[2]; }
+static inline V3 cross3(const V3& a, const V3& b) {
+  return V3{{a.v[1] * b.v[2] - a.v[2] * b.v[1], a.v[2] * b.v[0] - a.v[0] * b.v[2], a.v[0] * b.v[1] - a.v[1] * b.v[0]}};
+}
+static inline double m3_det(const M3& m) {
+  return m.a[0][0] * (m.a[1][1] * m.a[2][2] - m.a[1][2] * m.a[2][1]) -
+         m.a[0][1] * (m.a[1][0] * m.a[2][2] - m.a[1][2] * m.a[2][0]) +
+         m.a[0][2] * (m.a[1][0] * m.a[2][1] - m.a[1][1] * m.a[2][0]);
+}
+// Eigen's fixed-size 3x3 inverse: cofactors / determinant (Eigen/src/LU/InverseImpl.h,
+// compute_inverse_size3_helper) — restated, parity unpinned.
+static inline double cof(const M3& m, int i, int j) {
+  int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return m.a[i1][j1] * m.a[i2][j2] - m.a[i1][j2] * m.a[i2][j1];
+}
+static inline M3 m3_inv(const M3& m) {
+  double c00 = cof(m, 0, 0), c10 = cof(m, 1, 0), c20 = cof(m, 2, 0);
+  double det = c00 * m.a[0][0] + c10 * m.a[1][0] + c20 * m.a[2][0];
+  double invdet = 1.0 / det;
+  M3 r;
+  r.a[0][0] = c00 * invdet; r.a[0][1] = c10 * invdet; r.a[0][2] = c20 * invdet;
+  r.a[1][0] = cof(m, 0, 1) * invdet; r.a[1][1] = cof(m, 1, 1) * invdet; r.a[1][2] = cof(m, 2, 1) * invdet;
+  r.a[2][0] = cof(m, 0, 2) * invdet; r.a[2][1] = cof(m, 1, 2) * invdet; r.a[2][2] = cof(m, 2, 2) * invdet;
+  return r;
+}
+
+// ------------------------------------------------------------------ SE(3), Sophus conventions
+// pose7 = [qx,qy,qz,qw,tx,ty,tz]  (Sophus::SE3d::data(); Jacobian layout gicp_cost_function.h:64-70)
+struct SE3 { double q[4]; double t[3]; };  // q = x,y,z,w
+
+static inline SE3 se3_from7(const double* p) { SE3 T; for (int i = 0; i < 4; i++) T.q[i] = p[i]; for (int i = 0; i < 3; i++) T.t[i] = p[4 + i]; return T; }
+static inline void se3_to7(const SE3& T, double* p) { for (int i = 0; i < 4; i++) p[i] = T.q[i]; for (int i = 0; i < 3; i++) p[4 + i] = T.t[i]; }
+static inline SE3 se3_identity() { SE3 T{{0, 0, 0, 1}, {0, 0, 0}}; return T; }
+
+// Eigen::Quaternion::toRotationMatrix (formulas quoted in gicp_cost_function.h:110-120)
+static inline M3 quat_to_R(const double* q) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  M3 R;
+  R.a[0][0] = 1 - (tyy + tzz); R.a[0][1] = txy - twz;       R.a[0][2] = txz + twy;
+  R.a[1][0] = txy + twz;       R.a[1][1] = 1 - (txx + tzz); R.a[1][2] = tyz - twx;
+  R.a[2][0] = txz - twy;       R.a[2][1] = tyz + twx;       R.a[2][2] = 1 - (txx + tyy);
+  return R;
+}
+// q * p  (Eigen _transformVector / Sophus SO3::operator*(point))
+static inline V3 quat_rot(const double* q, const V3& p) {
+  V3 qv{{q[0], q[1], q[2]}};
+  V3 uv = cross3(qv, p);
+  uv.v[0] += uv.v[0]; uv.v[1] += uv.v[1]; uv.v[2] += uv.v[2];
+  V3 c2 = cross3(qv, uv);
+  return V3{{p.v[0] + q[3] * uv.v[0] + c2.v[0], p.v[1] + q[3] * uv.v[1] + c2.v[1], p.v[2] + q[3] * uv.v[2] + c2.v[2]}};
+}
+static inline void quat_mul(const double* a, const double* b, double* r) {
+  const double ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  r[3] = aw * bw - ax * bx - ay * by - az * bz;
+  r[0] = aw * bx + ax * bw + ay * bz - az * by;
+  r[1] = aw * by + ay * bw + az * bx - ax * bz;
+  r[2] = aw * bz + az * bw + ax * by - ay * bx;
+}
+static inline void quat_normalize(double* q) {
+  double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; i++) q[i] /= n;
+}
+static inline SE3 se3_mul(const SE3& A, const SE3& B) {  // Sophus SE3::operator*
+  SE3 C;
+  quat_mul(A.q, B.q, C.q);
+  quat_normalize(C.q);
+  V3 rb = quat_rot(A.q, V3{{B.t[0], B.t[1], B.t[2]}});
+  for (int i = 0; i < 3; i++) C.t[i] = A.t[i] + rb.v[i];
+  return C;
+}
+static inline SE3 se3_inv(const SE3& A) {  // Sophus SE3::inverse: (R^-1, R^-1 * (-t))
+  SE3 C;
+  C.q[0] = -A.q[0]; C.q[1] = -A.q[1]; C.q[2] = -A.q[2]; C.q[3] = A.q[3];
+  V3 r = quat_rot(C.q, V3{{-A.t[0], -A.t[1], -A.t[2]}});
+  for (int i = 0; i < 3; i++) C.t[i] = r.v[i];
+  return C;
+}
+static inline M3 hat(const double* w) {
+  M3 O = m3_zero();
+  O.a[0][1] = -w[2]; O.a[0][2] = w[1];
+  O.a[1][0] = w[2];  O.a[1][2] = -w[0];
+  O.a[2][0] = -w[1]; O.a[2][1] = w[0];
+  return O;
+}
+static const double kSophusEps = 1e-10;  // Sophus::Constants<double>::epsilon()
+
+// Sophus SE3::exp, tangent = (upsilon, omega) (translation first)
+static inline SE3 se3_exp(const double* d) {
+  const double* up = d; const double* om = d + 3;
+  SE3 T;
+  double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  double theta, imag, real;
+  if (th2 < kSophusEps * kSophusEps) {
+    theta = std::sqrt(th2);
+    double th4 = th2 * th2;
+    imag = 0.5 - (1.0 / 48.0) * th2 + (1.0 / 3840.0) * th4;
+    real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
+  } else {
+    theta = std::sqrt(th2);
+    double half = 0.5 * theta;
+    imag = std::sin(half) / theta;
+    real = std::cos(half);
+  }
+  T.q[0] = imag * om[0]; T.q[1] = imag * om[1]; T.q[2] = imag * om[2]; T.q[3] = real;
+  M3 Om = hat(om);
+  M3 V;
+  if (theta < kSophusEps) {
+    V = quat_to_R(T.q);  // Sophus uses so3.matrix() here
+  } else {
+    M3 Om2 = m3_mul(Om, Om);
+    double a = (1 - std::cos(theta)) / th2;
+    double b = (theta - std::sin(theta)) / (th2 * theta);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) V.a[i][j] = (i == j ? 1.0 : 0.0) + a * Om.a[i][j] + b * Om2.a[i][j];
+  }
+  V3 t = m3_v(V, V3{{up[0], up[1], up[2]}});
+  T.t[0] = t.v[0]; T.t[1] = t.v[1]; T.t[2] = t.v[2];
+  return T;
+}
+// Sophus SE3::log → (upsilon, omega)
+static inline void se3_log(const SE3& T, double* out) {
+  const double* q = T.q;
+  double sq_n = q[0] * q[0] + q[1] * q[1] + q[2] * q[2];
+  double w = q[3];
+  double two_atan_nbyw_by_n, theta;
+  if (sq_n < kSophusEps * kSophusEps) {
+    double sq_w = w * w;
+    two_atan_nbyw_by_n = 2.0 / w - (2.0 / 3.0) * sq_n / (w * sq_w);
+    theta = 2.0 * sq_n / w;
+  } else {
+    double n = std::sqrt(sq_n);
+    // equivalent to atan(n/w) up to the 2*pi ambiguity; Sophus picks the (-pi, pi] branch
+    double atan_nbyw = (w < 0) ? std::atan2(-n, -w) : std::atan2(n, w);
+    two_atan_nbyw_by_n = 2.0 * atan_nbyw / n;
+    theta = two_atan_nbyw_by_n * n;
+  }
+  double om[3] = {two_atan_nbyw_by_n * q[0], two_atan_nbyw_by_n * q[1], two_atan_nbyw_by_n * q[2]};
+  M3 Om = hat(om);
+  M3 Om2 = m3_mul(Om, Om);
+  M3 Vi;
+  if (std::fabs(theta) < kSophusEps) {
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Vi.a[i][j] = (i == j ? 1.0 : 0.0) - 0.5 * Om.a[i][j] + (1.0 / 12.0) * Om2.a[i][j];
+  } else {
+    double half = 0.5 * theta;
+    double c = (1.0 - theta * std::cos(half) / (2.0 * std::sin(half))) / (theta * theta);
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Vi.a[i][j] = (i == j ? 1.0 : 0.0) - 0.5 * Om.a[i][j] + c * Om2.a[i][j];
+  }
+  V3 up = m3_v(Vi, V3{{T.t[0], T.t[1], T.t[2]}});
+  out[0] = up.v[0]; out[1] = up.v[1]; out[2] = up.v[2];
+  out[3] = om[0]; out[4] = om[1]; out[5] = om[2];
+}
+// local_parameterization_se3.h:17-24  Plus: T * exp(delta)
+static inline SE3 se3_plus(const SE3& T, const double* delta) { return se3_mul(T, se3_exp(delta)); }
+// local_parameterization_se3.h:30-36 → Sophus SE3::Dx_this_mul_exp_x_at_0 : 7x6, row-major,
+// rows [qx,qy,qz,qw,tx,ty,tz], cols [ups(3), omega(3)]
+static inline void se3_dx_this_mul_exp_x_at_0(const SE3& T, double J[7][6]) {
+  for (int i = 0; i < 7; i++) for (int j = 0; j < 6; j++) J[i][j] = 0;
+  const double x = T.q[0], y = T.q[1], z = T.q[2], w = T.q[3];
+  // quaternion rows w.r.t. omega : 0.5 * [[w,-z,y],[z,w,-x],[-y,x,w],[-x,-y,-z]]
+  J[0][3] = 0.5 * w;  J[0][4] = -0.5 * z; J[0][5] = 0.5 * y;
+  J[1][3] = 0.5 * z;  J[1][4] = 0.5 * w;  J[1][5] = -0.5 * x;
+  J[2][3] = -0.5 * y; J[2][4] = 0.5 * x;  J[2][5] = 0.5 * w;
+  J[3][3] = -0.5 * x; J[3][4] = -0.5 * y; J[3][5] = -0.5 * z;
+  // translation rows w.r.t. upsilon : R (written as Sophus does, from quaternion products)
+  const double ww = w * w, xx = x * x, yy = y * y, zz = z * z;
+  const double wz2 = 2 * w * z, xy2 = 2 * x * y, wy2 = 2 * w * y, xz2 = 2 * x * z, wx2 = 2 * w * x, yz2 = 2 * y * z;
+  J[4][0] = -yy - zz + ww + xx; J[4][1] = -wz2 + xy2;        J[4][2] = wy2 + xz2;
+  J[5][0] = wz2 + xy2;          J[5][1] = -zz + (ww - xx) + yy; J[5][2] = -wx2 + yz2;
+  J[6][0] = -wy2 + xz2;         J[6][1] = wx2 + yz2;         J[6][2] = -yy + zz + (ww - xx);
+}
+
+// ------------------------------------------------------------------ Eigen::JacobiSVD<Matrix3d> (U only)
+// Two-sided Jacobi as in Eigen/src/SVD/JacobiSVD.h + Jacobi/Jacobi.h (restated; parity unpinned).
+struct Rot { double c, s; };
+static inline bool make_jacobi(double x, double y, double z, Rot* r) {
+  double deno = 2.0 * std::fabs(y);
+  if (deno < std::numeric_limits<double>::min()) { r->c = 1; r->s = 0; return false; }
+  double tau = (x - z) / deno;
+  double w = std::sqrt(tau * tau + 1.0);
+  double t = (tau > 0) ? 1.0 / (tau + w) : 1.0 / (tau - w);
+  double sign_t = t > 0 ? 1.0 : -1.0;
+  double n = 1.0 / std::sqrt(t * t + 1.0);
+  r->s = -sign_t * (y / std::fabs(y)) * std::fabs(t) * n;
+  r->c = n;
+  return true;
+}
+static inline void rot_rows(M3& W, int p, int q, Rot j) {  // applyOnTheLeft(p,q,j)
+  for (int i = 0; i < 3; i++) {
+    double xi = W.a[p][i], yi = W.a[q][i];
+    W.a[p][i] = j.c * xi + j.s * yi;
+    W.a[q][i] = -j.s * xi + j.c * yi;
+  }
+}
+static inline void rot_cols(M3& W, int p, int q, Rot j) {  // applyOnTheRight(p,q,j): uses j.transpose()
+  for (int i = 0; i < 3; i++) {
+    double xi = W.a[i][p], yi = W.a[i][q];
+    W.a[i][p] = j.c * xi - j.s * yi;
+    W.a[i][q] = j.s * xi + j.c * yi;
+  }
+}
+static void jacobi_svd_U(const M3& Ain, M3* Uout, double sv[3]) {
+  const double precision = 2.0 * std::numeric_limits<double>::epsilon();
+  const double considerAsZero = std::numeric_limits<double>::min();
+  double scale = 0;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) scale = std::max(scale, std::fabs(Ain.a[i][j]));
+  if (!(scale > 0) || !std::isfinite(scale)) scale = 1.0;
+  M3 W;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) W.a[i][j] = Ain.a[i][j] / scale;
+  M3 U = m3_zero();
+  U.a[0][0] = U.a[1][1] = U.a[2][2] = 1.0;
+  double maxDiag = std::max(std::fabs(W.a[0][0]), std::max(std::fabs(W.a[1][1]), std::fabs(W.a[2][2])));
+  bool finished = false;
+  int guard = 0;
+  while (!finished && guard++ < 100) {
+    finished = true;
+    for (int p = 1; p < 3; p++) {
+      for (int q = 0; q < p; q++) {
+        double threshold = std::max(considerAsZero, precision * maxDiag);
+        if (std::fabs(W.a[p][q]) > threshold || std::fabs(W.a[q][p]) > threshold) {
+          finished = false;
+          // real_2x2_jacobi_svd
+          double m00 = W.a[p][p], m01 = W.a[p][q], m10 = W.a[q][p], m11 = W.a[q][q];
+          Rot rot1;
+          double t = m00 + m11, d = m10 - m01;
+          if (std::fabs(d) < std::numeric_limits<double>::min()) { rot1.s = 0; rot1.c = 1; }
+          else { double u = t / d; double tmp = std::sqrt(1.0 + u * u); rot1.s = 1.0 / tmp; rot1.c = u / tmp; }
+          // m.applyOnTheLeft(0,1,rot1)
+          double n00 = rot1.c * m00 + rot1.s * m10, n01 = rot1.c * m01 + rot1.s * m11;
+          double n11 = -rot1.s * m01 + rot1.c * m11;
+          Rot jr; make_jacobi(n00, n01, n11, &jr);
+          // j_left = rot1 * j_right.transpose()
+          Rot jrt{jr.c, -jr.s};
+          Rot jl{rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
+          rot_rows(W, p, q, jl);
+          Rot jlt{jl.c, -jl.s};
+          rot_cols(U, p, q, jlt);
+          rot_cols(W, p, q, jr);
+          maxDiag = std::max(maxDiag, std::max(std::fabs(W.a[p][p]), std::fabs(W.a[q][q])));
+        }
+      }
+    }
+  }
+  for (int i = 0; i < 3; i++) {
+    double a = std::fabs(W.a[i][i]);
+    sv[i] = a;
+    if (a != 0) { double s = W.a[i][i] / a; for (int r = 0; r < 3; r++) U.a[r][i] *= s; }
+  }
+  for (int i = 0; i < 3; i++) sv[i] *= scale;
+  for (int i = 0; i < 3; i++) {  // sort descending (selection, as Eigen)
+    int pos = i; double mx = sv[i];
+    for (int j = i + 1; j < 3; j++) if (sv[j] > mx) { mx = sv[j]; pos = j; }
+    if (mx == 0) break;
+    if (pos != i) {
+      std::swap(sv[i], sv[pos]);
+      for (int r = 0; r < 3; r++) std::swap(U.a[r][i], U.a[r][pos]);
+    }
+  }
+  *Uout = U;
+}
+
+// ------------------------------------------------------------------ exact kNN
+// Contract: k targets minimising (d2_f32, index) lexicographically,
+// d2 = fl(fl(fl(dx*dx)+fl(dy*dy))+fl(dz*dz)), dx = fl(q.x - p.x)  (FLANN L2_Simple<float>).
+static inline float d2f(const float* q, const float* p) {
+  float dx = q[0] - p[0], dy = q[1] - p[1], dz = q[2] - p[2];
+  float r = dx * dx;
+  r = r + dy * dy;
+  r = r + dz * dz;
+  return r;
+}
+struct Cand { float d; int32_t i; };
+static inline bool cand_less(const Cand& a, const Cand& b) { return a.d < b.d || (a.d == b.d && a.i < b.i); }
+
+struct TopK {
+  int k, n = 0;
+  Cand* c;  // sorted ascending, capacity k
+  TopK(int k_, Cand* buf) : k(k_), c(buf) {}
+  inline float worst() const { return n < k ? std::numeric_limits<float>::infinity() : c[k - 1].d; }
+  inline void push(Cand x) {
+    if (n == k) { if (!cand_less(x, c[k - 1])) return; n--; }
+    int j = n++;
+    while (j > 0 && cand_less(x, c[j - 1])) { c[j] = c[j - 1]; j--; }
+    c[j] = x;
+  }
+};
+
+static void knn_brute(const float* T, int nt, const float* q, int k, Cand* out, int* nout) {
+  TopK tk(k, out);
+  for (int i = 0; i < nt; i++) tk.push(Cand{d2f(q, T + 3 * (size_t)i), i});
+  *nout = tk.n;
+}
+
+// kd-tree (stands in for pcl::KdTreeFLANN: gicp.h:45-46, em_icp.h:53-54, semantic_point_cloud.hpp:21-23).
+// Pruning uses only monotone-safe f32 lower bounds, so the answer equals knn_brute exactly.
+struct KdTree {
+  struct Node { int lo, hi, left, right; float bmin[3], bmax[3]; };
+  std::vector<Node> nodes;
+  std::vector<int32_t> idx;   // permutation
+  std::vector<float> pts;     // reordered copy, xyz
+  int n = 0;
+  static constexpr int kLeaf = 16;
+
+  void build(const float* xyz, int n_) {
+    n = n_;
+    idx.resize(n);
+    std::iota(idx.begin(), idx.end(), 0);
+    nodes.clear();
+    nodes.reserve(2 * (n / kLeaf + 2));
+    if (n > 0) build_rec(xyz, 0, n);
+    pts.resize(3 * (size_t)n);
+    for (int i = 0; i < n; i++) for (int c = 0; c < 3; c++) pts[3 * (size_t)i + c] = xyz[3 * (size_t)idx[i] + c];
+  }
+  int build_rec(const float* xyz, int lo, int hi) {
+    int me = (int)nodes.size();
+    nodes.push_back(Node());
+    Node nd; nd.lo = lo; nd.hi = hi; nd.left = nd.right = -1;
+    for (int c = 0; c < 3; c++) { nd.bmin[c] = std::numeric_limits<float>::infinity(); nd.bmax[c] = -nd.bmin[c]; }
+    for (int i = lo; i < hi; i++)
+      for (int c = 0; c < 3; c++) {
+        float v = xyz[3 * (size_t)idx[i] + c];
+        nd.bmin[c] = std::min(nd.bmin[c], v); nd.bmax[c] = std::max(nd.bmax[c], v);
+      }
+    if (hi - lo > kLeaf) {
+      int ax = 0; float ext = nd.bmax[0] - nd.bmin[0];
+      for (int c = 1; c < 3; c++) if (nd.bmax[c] - nd.bmin[c] > ext) { ext = nd.bmax[c] - nd.bmin[c]; ax = c; }
+      int mid = (lo + hi) / 2;
+      std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
+        float va = xyz[3 * (size_t)a + ax], vb = xyz[3 * (size_t)b + ax];
+        return va < vb || (va == vb && a < b);
+      });
+      nd.left = build_rec(xyz, lo, mid);
+      nd.right = build_rec(xyz, mid, hi);
+    }
+    nodes[me] = nd;
+    return me;
+  }
+  static inline float box_lb(const Node& nd, const float* q) {  // same op sequence as d2f ⇒ lower bound in f32
+    float r = 0;
+    for (int c = 0; c < 3; c++) {
+      float d = 0.f;
+      if (q[c] < nd.bmin[c]) d = nd.bmin[c] - q[c];
+      else if (q[c] > nd.bmax[c]) d = q[c] - nd.bmax[c];
+      float s = d * d;
+      r = (c == 0) ? s : r + s;
+    }
+    return r;
+  }
+  void search_rec(int ni, const float* q, TopK& tk) const {
+    const Node& nd = nodes[ni];
+    if (nd.left < 0) {
+      for (int i = nd.lo; i < nd.hi; i++) tk.push(Cand{d2f(q, &pts[3 * (size_t)i]), idx[i]});
+      return;
+    }
+    float bl = box_lb(nodes[nd.left], q), br = box_lb(nodes[nd.right], q);
+    int first = nd.left, second = nd.right; float b1 = bl, b2 = br;
+    if (br < bl) { std::swap(first, second); std::swap(b1, b2); }
+    if (!(b1 > tk.worst())) search_rec(first, q, tk);
+    if (!(b2 > tk.worst())) search_rec(second, q, tk);
+  }
+  void knn(const float* q, int k, Cand* out, int* nout) const {
+    TopK tk(k, out);
+    if (n > 0) search_rec(0, q, tk);
+    *nout = tk.n;
+  }
+};
+
+// ------------------------------------------------------------------ A.1 transform (pcl::transformPointCloud<PointT,double>)
+static inline void transform_point(const M3& R, const double* t, const float* p, float* o) {
+  double x = p[0], y = p[1], z = p[2];
+  o[0] = static_cast<float>(R.a[0][0] * x + R.a[0][1] * y + R.a[0][2] * z + t[0]);
+  o[1] = static_cast<float>(R.a[1][0] * x + R.a[1][1] * y + R.a[1][2] * z + t[1]);
+  o[2] = static_cast<float>(R.a[2][0] * x + R.a[2][1] * y + R.a[2][2] * z + t[2]);
+}
+
+// ------------------------------------------------------------------ covariances (gicp.hpp:177-239; em_icp.hpp:270-344;
+//                                                                     semantic_point_cloud.hpp:25-84)
+static void covariances(const float* xyz, const uint32_t* labels, int n, const KdTree& tree, int k, double eps,
+                        int N, double* cov_out /*n*9*/, double* dist_out /*n*N or null*/, double* normal_out /*n*3 or null*/,
+                        int32_t* nn_out /*n*k or null*/, int threads) {
+  const double increment = 1.0 / static_cast<double>(k);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+  for (int it = 0; it < n; it++) {
+    std::vector<Cand> buf(k);
+    int nn = 0;
+    tree.knn(xyz + 3 * (size_t)it, k, buf.data(), &nn);
+    double mean[3] = {0, 0, 0};
+    double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    std::vector<double> dist;
+    if (N > 0) dist.assign(N, 0.0);
+    for (int j = 0; j < nn; j++) {
+      int index = buf[j].i;
+      const float* pt = xyz + 3 * (size_t)index;
+      if (N > 0) dist[labels[index] - 1] += increment;  // em_icp.hpp:301
+      mean[0] += pt[0]; mean[1] += pt[1]; mean[2] += pt[2];
+      // products are float*float rounded to float, then widened (gicp.hpp:205-212)
+      cov[0][0] += pt[0] * pt[0];
+      cov[1][0] += pt[1] * pt[0];
+      cov[1][1] += pt[1] * pt[1];
+      cov[2][0] += pt[2] * pt[0];
+      cov[2][1] += pt[2] * pt[1];
+      cov[2][2] += pt[2] * pt[2];
+    }
+    for (int c = 0; c < 3; c++) mean[c] /= static_cast<double>(k);  // divisor is k even if nn<k
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b <= a; b++) {
+        cov[a][b] /= static_cast<double>(k);
+        cov[a][b] -= mean[a] * mean[b];
+        cov[b][a] = cov[a][b];
+      }
+    M3 C; std::memcpy(C.a, cov, sizeof cov);
+    M3 U; double sv[3];
+    jacobi_svd_U(C, &U, sv);
+    double out[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int c = 0; c < 3; c++) {
+      double v = (c == 2) ? eps : 1.0;
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) out[a][b] += (v * U.a[a][c]) * U.a[b][c];
+    }
+    std::memcpy(cov_out + 9 * (size_t)it, out, sizeof out);
+    if (normal_out) for (int a = 0; a < 3; a++) normal_out[3 * (size_t)it + a] = U.a[a][2];
+    if (dist_out && N > 0) std::memcpy(dist_out + (size_t)N * it, dist.data(), sizeof(double) * N);
+    if (nn_out) for (int j = 0; j < k; j++) nn_out[(size_t)k * it + j] = j < nn ? buf[j].i : -1;
+  }
+}
+
+// ------------------------------------------------------------------ GICPCostFunction (gicp_cost_function.h)
+struct CostFn {
+  V3 ps, pt;  // f32 values widened (ctor :21-22)
+  M3 cs, ct;
+};
+// Evaluate (:27-73). jac7 layout [qx,qy,qz,qw,tx,ty,tz].
+static inline double cost_evaluate(const CostFn& f, const SE3& T, double* jac7) {
+  M3 R = quat_to_R(T.q);
+  M3 M = m3_inv(m3_add(f.ct, m3_mul(m3_mul(R, f.cs), m3_T(R))));
+  V3 tp = quat_rot(T.q, f.ps);
+  for (int i = 0; i < 3; i++) tp.v[i] += T.t[i];
+  V3 res{{f.pt.v[0] - tp.v[0], f.pt.v[1] - tp.v[1], f.pt.v[2] - tp.v[2]}};
+  V3 dT = m3_v(M, res);
+  double r = dot3(res, dT);
+  if (jac7) {
+    M3 Ta = m3_inv(m3_add(m3_T(f.ct), m3_mul(m3_mul(R, m3_T(f.cs)), m3_T(R))));
+    V3 tb = m3_v(M, res);
+    V3 tc = m3_v(Ta, res);
+    V3 r1 = vT_m3(vT_m3(vT_m3(res, Ta), R), m3_T(f.cs));  // res^T Ta R cs^T
+    V3 r2 = vT_m3(vT_m3(vT_m3(res, M), R), f.cs);          // res^T M R cs
+    M3 dR;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        dR.a[i][j] = -(tb.v[i] * f.ps.v[j] + tc.v[i] * r1.v[j] + tb.v[i] * r2.v[j] + tc.v[i] * f.ps.v[j]);
+    // dRtodq (:98-176)
+    const double qx = T.q[0], qy = T.q[1], qz = T.q[2], qw = T.q[3];
+    const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, tw = 2 * qw;
+    const double mfx = -2 * tx, mfy = -2 * ty, mfz = -2 * tz, mtw = -1 * tw;
+    double dRdw[3][3] = {{0, -tz, ty}, {tz, 0, -tx}, {-ty, tx, 0}};
+    double dRdx[3][3] = {{0, ty, tz}, {ty, mfx, mtw}, {tz, tw, mfx}};
+    double dRdy[3][3] = {{mfy, tx, tw}, {tx, 0, tz}, {mtw, tz, mfy}};
+    double dRdz[3][3] = {{mfz, mtw, tx}, {tw, mfz, ty}, {tx, ty, 0}};
+    auto tr = [&](double D[3][3]) {  // trace(dR^T * D) = sum_ij dR_ij D_ij
+      double s = 0;
+      for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) s += dR.a[i][j] * D[i][j];
+      return s;
+    };
+    jac7[3] = tr(dRdw); jac7[0] = tr(dRdx); jac7[1] = tr(dRdy); jac7[2] = tr(dRdz);
+    jac7[4] = -2.0 * dT.v[0]; jac7[5] = -2.0 * dT.v[1]; jac7[6] = -2.0 * dT.v[2];
+  }
+  return r;
+}
+// Probability (:75-87) — declared bool: the density is converted to bool.
+static inline double cost_probability_density(const CostFn& f, const SE3& T) {
+  M3 R = quat_to_R(T.q);
+  M3 cov = m3_add(f.ct, m3_mul(m3_mul(R, f.cs), m3_T(R)));
+  M3 M = m3_inv(cov);
+  V3 tp = quat_rot(T.q, f.ps);
+  for (int i = 0; i < 3; i++) tp.v[i] += T.t[i];
+  V3 res{{f.pt.v[0] - tp.v[0], f.pt.v[1] - tp.v[1], f.pt.v[2] - tp.v[2]}};
+  V3 dT = m3_v(M, res);
+  double mahal = -1.0 / 2.0 * dot3(res, dT);
+  M3 c2 = cov;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) c2.a[i][j] = (2 * M_PI) * cov.a[i][j];
+  return std::pow(m3_det(c2), -1.0 / 2.0) * std::exp(mahal);
+}
+static inline bool cost_probability(const CostFn& f, const SE3& T) { return static_cast<bool>(cost_probability_density(f, T)); }
+
+// local (6-dof) Jacobian the way Ceres forms it: J7 (1x7) * ComputeJacobian (7x6)
+static inline void local_jacobian(const double* jac7, const SE3& T, double* jac6) {
+  double P[7][6];
+  se3_dx_this_mul_exp_x_at_0(T, P);
+  for (int j = 0; j < 6; j++) {
+    double s = 0;
+    for (int i = 0; i < 7; i++) s += jac7[i] * P[i][j];
+    jac6[j] = s;
+  }
+}
+
+// ------------------------------------------------------------------ losses (Ceres loss_function.cc, restated; sqloss.h)
+enum LossKind { LOSS_GICP = 0, LOSS_SEMANTIC = 1, LOSS_EM = 2 };
+static inline void cauchy(double a, double s, double rho[3]) {
+  const double b = a * a, c = 1.0 / b;
+  const double sum = 1.0 + s * c, inv = 1.0 / sum;
+  rho[0] = b * std::log(sum);
+  rho[1] = std::max(std::numeric_limits<double>::min(), inv);
+  rho[2] = -c * (inv * inv);
+}
+static inline void sqloss(double s, double rho[3]) {
+  double v = s + std::numeric_limits<double>::epsilon();
+  rho[0] = std::sqrt(v);
+  rho[1] = 1.0 / (2.0 * std::sqrt(v));
+  rho[2] = -1.0 / (4.0 * std::pow(v, 1.5));
+}
+static inline void loss_eval(int kind, double w, double s, double rho[3]) {
+  if (kind == LOSS_SEMANTIC) { cauchy(1.5, s, rho); return; }  // semantic_icp.hpp:96
+  double g[3], f[3];
+  sqloss(s, g);               // ComposedLoss(f, g): g first
+  cauchy(3.0, g[0], f);       // gicp.hpp:98-104 ; em_icp.hpp:109-117
+  if (kind == LOSS_EM) { f[0] *= w; f[1] *= w; f[2] *= w; }  // ScaledLoss
+  rho[0] = f[0];
+  rho[1] = f[1] * g[1];
+  rho[2] = f[2] * g[1] * g[1] + f[1] * g[2];
+}
+
+// ------------------------------------------------------------------ problem + Ceres-like trust-region LM
+struct Residual { int s, t; double w; };
+struct Problem {
+  const float* sxyz; const double* scov;
+  const float* txyz; const double* tcov;
+  std::vector<Residual> res;
+  int loss;
+};
+struct Eval { double cost; double H[6][6]; double g[6]; };
+
+static inline CostFn make_costfn(const Problem& P, const Residual& r) {
+  CostFn f;
+  for (int c = 0; c < 3; c++) { f.ps.v[c] = P.sxyz[3 * (size_t)r.s + c]; f.pt.v[c] = P.txyz[3 * (size_t)r.t + c]; }
+  std::memcpy(f.cs.a, P.scov + 9 * (size_t)r.s, sizeof f.cs.a);
+  std::memcpy(f.ct.a, P.tcov + 9 * (size_t)r.t, sizeof f.ct.a);
+  return f;
+}
+static void evaluate(const Problem& P, const SE3& T, bool jac, Eval* E, int threads) {
+  const int n = (int)P.res.size();
+#ifdef _OPENMP
+  int nt = std::max(1, threads);
+#else
+  int nt = 1;
+#endif
+  std::vector<Eval> part(nt);
+  for (auto& e : part) std::memset(&e, 0, sizeof e);
+#pragma omp parallel num_threads(nt)
+  {
+#ifdef _OPENMP
+    int tid = omp_get_thread_num();
+#else
+    int tid = 0;
+#endif
+    Eval& e = part[tid];
+#pragma omp for schedule(static)
+    for (int i = 0; i < n; i++) {
+      CostFn f = make_costfn(P, P.res[i]);
+      double j7[7], j6[6];
+      double r = cost_evaluate(f, T, jac ? j7 : nullptr);
+      double rho[3];
+      loss_eval(P.loss, P.res[i].w, r * r, rho);
+      e.cost += 0.5 * rho[0];
+      if (jac) {
+        // Ceres Corrector with rho[2] <= 0: residual and Jacobian row scaled by sqrt(rho[1])
+        double sr = std::sqrt(rho[1]);
+        local_jacobian(j7, T, j6);
+        double rc = sr * r;
+        for (int a = 0; a < 6; a++) j6[a] *= sr;
+        for (int a = 0; a < 6; a++) {
+          e.g[a] += j6[a] * rc;
+          for (int b = 0; b <= a; b++) e.H[a][b] += j6[a] * j6[b];
+        }
+      }
+    }
+  }
+  std::memset(E, 0, sizeof *E);
+  for (int t = 0; t < nt; t++) {
+    E->cost += part[t].cost;
+    for (int a = 0; a < 6; a++) { E->g[a] += part[t].g[a]; for (int b = 0; b <= a; b++) E->H[a][b] += part[t].H[a][b]; }
+  }
+  for (int a = 0; a < 6; a++) for (int b = 0; b < a; b++) E->H[b][a] = E->H[a][b];
+}
+// 6x6 SPD solve by Cholesky (stands in for DENSE_QR on the stacked [J;D] system — same minimiser)
+static bool chol_solve6(const double A[6][6], const double* b, double* x) {
+  double L[6][6] = {};
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) {
+      double s = A[i][j];
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) { if (!(s > 0)) return false; L[i][i] = std::sqrt(s); }
+      else L[i][j] = s / L[j][j];
+    }
+  double y[6];
+  for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[i][k] * y[k]; y[i] = s / L[i][i]; }
+  for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k]; x[i] = s / L[i][i]; }
+  return true;
+}
+struct LMStats { int iterations = 0, successful = 0, termination = 0; double initial_cost = 0, final_cost = 0; };
+enum { TERM_NO_CONV = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_RADIUS = 4, TERM_FAIL = 5, TERM_EMPTY = 6 };
+
+static LMStats lm_solve(const Problem& P, SE3* x, int threads) {
+  LMStats st;
+  if (P.res.empty()) { st.termination = TERM_EMPTY; return st; }  // Ceres: nothing to optimise, pose unchanged
+  const double gtol = 0.1 * kSophusEps, ftol = 0.1 * kSophusEps, ptol = 1e-8;  // gicp.hpp:139-140
+  const int max_iter = 400;                                                      // gicp.hpp:143
+  const double min_rel_decrease = 1e-3, max_radius = 1e16, min_radius = 1e-32, min_diag = 1e-6, max_diag = 1e32;
+  double radius = 1e4, decrease_factor = 2.0;
+  bool reuse_diag = false;
+  Eval E;
+  evaluate(P, *x, true, &E, threads);
+  st.initial_cost = E.cost;
+  double scale[6];
+  for (int j = 0; j < 6; j++) scale[j] = 1.0 / (1.0 + std::sqrt(E.H[j][j]));
+  auto grad_max_norm = [&](const SE3& T, const double* g) {
+    double ng[6]; for (int j = 0; j < 6; j++) ng[j] = -g[j];
+    SE3 Pj = se3_plus(T, ng);
+    double a7[7], b7[7]; se3_to7(T, a7); se3_to7(Pj, b7);
+    double m = 0; for (int i = 0; i < 7; i++) m = std::max(m, std::fabs(a7[i] - b7[i]));
+    return m;
+  };
+  auto norm7 = [](const SE3& T) { double a[7]; se3_to7(T, a); double s = 0; for (double v : a) s += v * v; return std::sqrt(s); };
+  double gmax = grad_max_norm(*x, E.g);
+  double x_norm = norm7(*x);
+  double cost = E.cost;
+  bool last_successful = true;
+  double diag[6];
+  int invalid = 0;
+  int iter = 0;
+  for (;;) {
+    if (iter >= max_iter) { st.termination = TERM_NO_CONV; break; }
+    if (last_successful && gmax <= gtol) { st.termination = TERM_GRADIENT; break; }
+    if (radius <= min_radius) { st.termination = TERM_RADIUS; break; }
+    iter++;
+    double Hs[6][6], gs[6];
+    for (int a = 0; a < 6; a++) { gs[a] = E.g[a] * scale[a]; for (int b = 0; b < 6; b++) Hs[a][b] = E.H[a][b] * scale[a] * scale[b]; }
+    if (!reuse_diag) for (int j = 0; j < 6; j++) diag[j] = std::min(std::max(Hs[j][j], min_diag), max_diag);
+    double A[6][6];
+    for (int a = 0; a < 6; a++) for (int b = 0; b < 6; b++) A[a][b] = Hs[a][b];
+    for (int j = 0; j < 6; j++) A[j][j] += diag[j] / radius;
+    double y[6];
+    bool ok = chol_solve6(A, gs, y);
+    reuse_diag = true;
+    double step[6], model = 0;
+    if (ok) {
+      for (int j = 0; j < 6; j++) step[j] = -y[j];
+      double sg = 0, sHs = 0;
+      for (int a = 0; a < 6; a++) { sg += step[a] * gs[a]; for (int b = 0; b < 6; b++) sHs += step[a] * Hs[a][b] * step[b]; }
+      model = -sg - 0.5 * sHs;
+    }
+    if (!ok || !(model > 0)) {
+      if (++invalid >= 5) { st.termination = TERM_FAIL; break; }
+      radius /= decrease_factor; decrease_factor *= 2.0; last_successful = false;
+      continue;
+    }
+    invalid = 0;
+    double delta[6];
+    for (int j = 0; j < 6; j++) delta[j] = step[j] * scale[j];
+    SE3 cand = se3_plus(*x, delta);
+    Eval Ec;
+    evaluate(P, cand, false, &Ec, threads);
+    double a7[7], b7[7]; se3_to7(*x, a7); se3_to7(cand, b7);
+    double sn = 0; for (int i = 0; i < 7; i++) sn += (a7[i] - b7[i]) * (a7[i] - b7[i]);
+    sn = std::sqrt(sn);
+    if (sn <= ptol * (x_norm + ptol)) { st.termination = TERM_PARAMETER; break; }
+    double cost_change = cost - Ec.cost;
+    if (std::fabs(cost_change) <= ftol * cost) { st.termination = TERM_FUNCTION; break; }
+    double rel = cost_change / model;
+    if (rel > min_rel_decrease) {
+      *x = cand; x_norm = norm7(*x);
+      evaluate(P, *x, true, &E, threads);
+      cost = E.cost;
+      gmax = grad_max_norm(*x, E.g);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
+      radius = std::min(max_radius, radius);
+      decrease_factor = 2.0; reuse_diag = false; last_successful = true; st.successful++;
+    } else {
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diag = true; last_successful = false;
+    }
+  }
+  st.iterations = iter;
+  st.final_cost = cost;
+  return st;
+}
+
+}  // namespace orc
+
+// =====================================================================================
+// C ABI for ctypes
+// =====================================================================================
+using namespace orc;
+
+extern "C" {
+
+struct orc_trace {      // optional per-pass trace (arrays sized by caller: max_passes)
+  int max_passes;
+  double* pose7;        // [max_passes][7]  pose after each pass
+  int* lm_iters;        // [max_passes]
+  int* n_res;           // [max_passes]     residual blocks with non-zero weight
+  double* cost;         // [max_passes]     final LM cost
+  int32_t* corr0;       // first pass: [ns*kc] target index or -1 (gated)
+  double* w0;           // first pass: [ns*kc] weights
+  float* d20;           // first pass: [ns*kc] squared distances
+};
+struct orc_result { double pose7[7]; int outer_iter; int lm_iters_total; double final_cost; int n_corr_last; double seconds; };
+
+int orc_num_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void orc_knn(const float* tgt, int nt, const float* q, int nq, int k, int32_t* idx, float* d2, int brute, int threads) {
+  KdTree tree;
+  if (!brute) tree.build(tgt, nt);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads > 0 ? threads : 1)
+  for (int i = 0; i < nq; i++) {
+    std::vector<Cand> buf(k);
+    int nn = 0;
+    if (brute) knn_brute(tgt, nt, q + 3 * (size_t)i, k, buf.data(), &nn);
+    else tree.knn(q + 3 * (size_t)i, k, buf.data(), &nn);
+    for (int j = 0; j < k; j++) {
+      idx[(size_t)i * k + j] = j < nn ? buf[j].i : -1;
+      d2[(size_t)i * k + j] = j < nn ? buf[j].d : std::numeric_limits<float>::infinity();
+    }
+  }
+}
+
+void orc_transform_points(const double* pose7, const float* xyz, int n, float* out) {
+  SE3 T = se3_from7(pose7);
+  M3 R = quat_to_R(T.q);
+  for (int i = 0; i < n; i++) transform_point(R, T.t, xyz + 3 * (size_t)i, out + 3 * (size_t)i);
+}
+
+void orc_covariances(const float* xyz, const uint32_t* labels, int n, int k, double eps, int N, double* cov, double* dist,
+                     double* normals, int32_t* nn, int threads) {
+  KdTree tree; tree.build(xyz, n);
+  covariances(xyz, labels, n, tree, k, eps, N, cov, dist, normals, nn, threads > 0 ? threads : 1);
+}
+
+void orc_jacobi_svd(const double* A9, double* U9, double* sv3) {
+  M3 A; std::memcpy(A.a, A9, sizeof A.a);
+  M3 U; jacobi_svd_U(A, &U, sv3);
+  std::memcpy(U9, U.a, sizeof U.a);
+}
+
+// residual, 1x7 Jacobian, 6-dof local Jacobian, probability density (before bool conversion)
+void orc_cost_eval(const float* ps, const float* pt, const double* cs9, const double* ct9, const double* pose7, double* r,
+                   double* jac7, double* jac6, double* density) {
+  CostFn f;
+  for (int c = 0; c < 3; c++) { f.ps.v[c] = ps[c]; f.pt.v[c] = pt[c]; }
+  std::memcpy(f.cs.a, cs9, sizeof f.cs.a); std::memcpy(f.ct.a, ct9, sizeof f.ct.a);
+  SE3 T = se3_from7(pose7);
+  double j7[7];
+  *r = cost_evaluate(f, T, j7);
+  if (jac7) std::memcpy(jac7, j7, sizeof j7);
+  if (jac6) local_jacobian(j7, T, jac6);
+  if (density) *density = cost_probability_density(f, T);
+}
+void orc_loss(int kind, double w, double s, double* rho3) { loss_eval(kind, w, s, rho3); }
+void orc_se3_exp(const double* d6, double* pose7) { se3_to7(se3_exp(d6), pose7); }
+void orc_se3_log(const double* pose7, double* d6) { se3_log(se3_from7(pose7), d6); }
+void orc_se3_mul(const double* a7, const double* b7, double* c7) { se3_to7(se3_mul(se3_from7(a7), se3_from7(b7)), c7); }
+void orc_se3_inv(const double* a7, double* c7) { se3_to7(se3_inv(se3_from7(a7)), c7); }
+void orc_se3_plus(const double* a7, const double* d6, double* c7) { se3_to7(se3_plus(se3_from7(a7), d6), c7); }
+void orc_se3_matrix(const double* a7, double* m16) {
+  SE3 T = se3_from7(a7); M3 R = quat_to_R(T.q);
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) m16[4 * i + j] = R.a[i][j]; m16[4 * i + 3] = T.t[i]; }
+  m16[12] = m16[13] = m16[14] = 0; m16[15] = 1;
+}
+void orc_se3_dx(const double* a7, double* J42) { double J[7][6]; se3_dx_this_mul_exp_x_at_0(se3_from7(a7), J); std::memcpy(J42, J, sizeof J); }
+
+// Evaluate Ceres-corrected cost / gradient / J^T J (upper+lower, 36) for an explicit correspondence list.
+void orc_eval_problem(const float* sxyz, const double* scov, const float* txyz, const double* tcov, const int32_t* s_idx,
+                      const int32_t* t_idx, const double* w, int nres, int loss, const double* pose7, double* cost,
+                      double* g6, double* H36, int threads) {
+  Problem P{sxyz, scov, txyz, tcov, {}, loss};
+  P.res.reserve(nres);
+  for (int i = 0; i < nres; i++) P.res.push_back(Residual{s_idx[i], t_idx[i], w ? w[i] : 1.0});
+  Eval E; evaluate(P, se3_from7(pose7), true, &E, threads > 0 ? threads : 1);
+  *cost = E.cost; std::memcpy(g6, E.g, sizeof E.g); std::memcpy(H36, E.H, sizeof E.H);
+}
+// One inner solve on an explicit correspondence list (what ceres::Solve does per outer pass).
+void orc_lm_solve(const float* sxyz, const double* scov, const float* txyz, const double* tcov, const int32_t* s_idx,
+                  const int32_t* t_idx, const double* w, int nres, int loss, double* pose7_inout, int* iters, int* term,
+                  double* final_cost, int threads) {
+  Problem P{sxyz, scov, txyz, tcov, {}, loss};
+  for (int i = 0; i < nres; i++) P.res.push_back(Residual{s_idx[i], t_idx[i], w ? w[i] : 1.0});
+  SE3 x = se3_from7(pose7_inout);
+  LMStats st = lm_solve(P, &x, threads > 0 ? threads : 1);
+  se3_to7(x, pose7_inout);
+  if (iters) *iters = st.iterations; if (term) *term = st.termination; if (final_cost) *final_cost = st.final_cost;
+}
+
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static inline double sq_log_step(const SE3& cur, const SE3& est) {  // gicp.hpp:153
+  double l[6]; se3_log(se3_mul(se3_inv(cur), est), l);
+  double s = 0; for (double v : l) s += v * v; return s;
+}
+
+// ---- GICP::align (gicp.hpp:29-175) ---------------------------------------------------
+void orc_align_gicp(const float* sxyz, int ns, const float* txyz, int nt, int k, double eps, const double* init7,
+                    orc_result* out, orc_trace* tr, int threads) {
+  threads = threads > 0 ? threads : 1;
+  double t0 = now_s();
+  KdTree stree, ttree; stree.build(sxyz, ns); ttree.build(txyz, nt);  // setSourceCloud/setTargetCloud gicp.h:42-63
+  std::vector<double> scov(9 * (size_t)ns), tcov(9 * (size_t)nt);
+  covariances(sxyz, nullptr, ns, stree, k, eps, 0, scov.data(), nullptr, nullptr, nullptr, threads);
+  covariances(txyz, nullptr, nt, ttree, k, eps, 0, tcov.data(), nullptr, nullptr, nullptr, threads);
+  SE3 cur = se3_from7(init7);
+  bool converged = false; size_t count = 0; int lm_total = 0; double fcost = 0; int ncorr = 0;
+  std::vector<float> tsrc(3 * (size_t)ns);
+  std::vector<int32_t> nn(ns); std::vector<float> nd(ns);
+  while (!converged) {
+    SE3 est = cur;
+    M3 R = quat_to_R(cur.q);
+    for (int i = 0; i < ns; i++) transform_point(R, cur.t, sxyz + 3 * (size_t)i, &tsrc[3 * (size_t)i]);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+    for (int i = 0; i < ns; i++) { Cand c; int m = 0; ttree.knn(&tsrc[3 * (size_t)i], 1, &c, &m); nn[i] = m ? c.i : -1; nd[i] = m ? c.d : INFINITY; }
+    Problem P{sxyz, scov.data(), txyz, tcov.data(), {}, LOSS_GICP};
+    for (int i = 0; i < ns; i++) if (nn[i] >= 0 && nd[i] < 250) P.res.push_back(Residual{i, nn[i], 1.0});
+    if (tr && count == 0 && tr->corr0) for (int i = 0; i < ns; i++) { bool g = nn[i] >= 0 && nd[i] < 250; tr->corr0[i] = g ? nn[i] : -1; if (tr->w0) tr->w0[i] = g ? 1.0 : 0.0; if (tr->d20) tr->d20[i] = nd[i]; }
+    LMStats st = lm_solve(P, &est, threads);
+    lm_total += st.iterations; fcost = st.final_cost; ncorr = (int)P.res.size();
+    double mse = sq_log_step(cur, est);
+    if (mse < 1e-5 || count > 50) converged = true;
+    cur = est;
+    if (tr && (int)count < tr->max_passes) { se3_to7(cur, tr->pose7 + 7 * count); tr->lm_iters[count] = st.iterations; tr->n_res[count] = ncorr; tr->cost[count] = fcost; }
+    count++;
+  }
+  se3_to7(cur, out->pose7); out->outer_iter = (int)count; out->lm_iters_total = lm_total; out->final_cost = fcost; out->n_corr_last = ncorr;
+  out->seconds = now_s() - t0;
+}
+
+// ---- EmIterativeClosestPoint<N>::align (em_icp.hpp:24-200) ---------------------------
+void orc_align_em(const float* sxyz, const uint32_t* slab, int ns, const float* txyz, const uint32_t* tlab, int nt, int N,
+                  const double* cm /*row-major NxN*/, int k, double eps, const double* init7, orc_result* out, orc_trace* tr,
+                  int threads) {
+  threads = threads > 0 ? threads : 1;
+  double t0 = now_s();
+  KdTree stree, ttree; stree.build(sxyz, ns); ttree.build(txyz, nt);
+  std::vector<double> scov(9 * (size_t)ns), tcov(9 * (size_t)nt), sdist((size_t)N * ns), tdist((size_t)N * nt);
+  covariances(sxyz, slab, ns, stree, k, eps, N, scov.data(), sdist.data(), nullptr, nullptr, threads);
+  covariances(txyz, tlab, nt, ttree, k, eps, N, tcov.data(), tdist.data(), nullptr, nullptr, threads);
+  SE3 cur = se3_from7(init7);
+  bool converged = false; size_t outer = 0; int lm_total = 0; double fcost = 0; int ncorr = 0;
+  const int KC = 4;
+  std::vector<float> tsrc(3 * (size_t)ns);
+  std::vector<int32_t> nn((size_t)KC * ns); std::vector<float> nd((size_t)KC * ns); std::vector<double> ww((size_t)KC * ns);
+  while (!converged) {
+    SE3 est = cur;
+    M3 R = quat_to_R(cur.q);
+    for (int i = 0; i < ns; i++) transform_point(R, cur.t, sxyz + 3 * (size_t)i, &tsrc[3 * (size_t)i]);
+    Problem P{sxyz, scov.data(), txyz, tcov.data(), {}, LOSS_EM};
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+    for (int i = 0; i < ns; i++) {
+      Cand c[KC]; int m = 0; ttree.knn(&tsrc[3 * (size_t)i], KC, c, &m);
+      for (int j = 0; j < KC; j++) {
+        size_t o = (size_t)KC * i + j;
+        nn[o] = -1; nd[o] = INFINITY; ww[o] = 0;
+        if (j >= m) continue;
+        nd[o] = c[j].d;
+        if (c[j].d < 250) {                         // em_icp.hpp:65
+          nn[o] = c[j].i;
+          const double* td = &tdist[(size_t)N * c[j].i];
+          const double* sd = &sdist[(size_t)N * i];
+          double prob = 0;                          // em_icp.hpp:84-89
+          for (int s = 0; s < N; s++) {
+            double a = 0, b = 0;
+            for (int r = 0; r < N; r++) { a += td[r] * cm[(size_t)r * N + s]; b += sd[r] * cm[(size_t)r * N + s]; }
+            prob += a * b;
+          }
+          Residual rr{i, c[j].i, 0};
+          CostFn f = make_costfn(P, rr);
+          prob *= cost_probability(f, est) ? 1.0 : 0.0;  // em_icp.hpp:108 (bool!)
+          ww[o] = prob;
+        }
+      }
+    }
+    for (int i = 0; i < ns; i++) for (int j = 0; j < KC; j++) { size_t o = (size_t)KC * i + j; if (nn[o] >= 0) P.res.push_back(Residual{i, nn[o], ww[o]}); }
+    if (tr && outer == 0 && tr->corr0) for (size_t o = 0; o < (size_t)KC * ns; o++) { tr->corr0[o] = nn[o]; if (tr->w0) tr->w0[o] = ww[o]; if (tr->d20) tr->d20[o] = nd[o]; }
+    LMStats st = lm_solve(P, &est, threads);
+    lm_total += st.iterations; fcost = st.final_cost; ncorr = (int)P.res.size();
+    double mse = sq_log_step(cur, est);
+    if (mse < 1e-5 || outer > 50) converged = true;
+    cur = est;
+    if (tr && (int)outer < tr->max_passes) { se3_to7(cur, tr->pose7 + 7 * outer); tr->lm_iters[outer] = st.iterations; tr->n_res[outer] = ncorr; tr->cost[outer] = fcost; }
+    outer++;
+  }
+  se3_to7(cur, out->pose7); out->outer_iter = (int)outer; out->lm_iters_total = lm_total; out->final_cost = fcost; out->n_corr_last = ncorr;
+  out->seconds = now_s() - t0;
+}
+
+// ---- getFusedLabels (em_icp.hpp:202-268) ---------------------------------------------
+void orc_fused_labels(const float* sxyz, const uint32_t* slab, int ns, const float* txyz, const uint32_t* tlab, int nt, int N,
+                      const double* cm, int k, double eps, const double* pose7, uint32_t* labels_out, int threads) {
+  threads = threads > 0 ? threads : 1;
+  KdTree stree, ttree; stree.build(sxyz, ns); ttree.build(txyz, nt);
+  std::vector<double> scov(9 * (size_t)ns), tcov(9 * (size_t)nt), sdist((size_t)N * ns), tdist((size_t)N * nt);
+  covariances(sxyz, slab, ns, stree, k, eps, N, scov.data(), sdist.data(), nullptr, nullptr, threads);
+  covariances(txyz, tlab, nt, ttree, k, eps, N, tcov.data(), tdist.data(), nullptr, nullptr, threads);
+  SE3 T = se3_from7(pose7);
+  M3 R = quat_to_R(T.q);
+  Problem P{sxyz, scov.data(), txyz, tcov.data(), {}, LOSS_EM};
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+  for (int i = 0; i < ns; i++) {
+    float q[3]; transform_point(R, T.t, sxyz + 3 * (size_t)i, q);
+    Cand c[4]; int m = 0; ttree.knn(q, 4, c, &m);
+    std::vector<double> sprob(N, 0.0);
+    for (int j = 0; j < m; j++) {
+      if (c[j].d < 250) {
+        CostFn f = make_costfn(P, Residual{i, c[j].i, 0});
+        double prob = cost_probability(f, T) ? 1.0 : 0.0;
+        const double* td = &tdist[(size_t)N * c[j].i];
+        const double* sd = &sdist[(size_t)N * i];
+        for (int s = 0; s < N; s++) {
+          double a = 0, b = 0;
+          for (int r = 0; r < N; r++) { a += td[r] * cm[(size_t)r * N + s]; b += sd[r] * cm[(size_t)r * N + s]; }
+          sprob[s] += (a * b) * prob;
+        }
+      }
+    }
+    double mx = 0; size_t ms = 0;
+    for (int s = 0; s < N; s++) if (sprob[s] > mx) { ms = s; mx = sprob[s]; }
+    labels_out[i] = (uint32_t)(ms + 1);
+  }
+}
+
+// ---- pcl_2_semantic (pcl_2_semantic.h:14-42): first-appearance label order, stable split ----
+// Returns number of classes; class_labels[c], class_start[c..c+1] index into order[] (original indices).
+int orc_label_split(const uint32_t* labels, int n, uint32_t* class_labels, int* class_start, int32_t* order) {
+  std::vector<uint32_t> labs; std::map<uint32_t, std::vector<int32_t>> mp;
+  for (int i = 0; i < n; i++) { if (mp.find(labels[i]) == mp.end()) labs.push_back(labels[i]); mp[labels[i]].push_back(i); }
+  int o = 0;
+  for (size_t c = 0; c < labs.size(); c++) { class_labels[c] = labs[c]; class_start[c] = o; for (int32_t i : mp[labs[c]]) order[o++] = i; }
+  class_start[labs.size()] = o;
+  return (int)labs.size();
+}
+
+// ---- SemanticIterativeClosestPoint::align (semantic_icp.hpp:27-166) -------------------
+// Input: PointXYZL-style clouds; split per pcl_2_semantic; per-class kd-trees and per-class covariances
+// (semantic_point_cloud.hpp:12-87) are built BEFORE the timed region in the reference; `seconds` here covers all.
+void orc_align_semantic(const float* sxyz, const uint32_t* slab, int ns, const float* txyz, const uint32_t* tlab, int nt, int k,
+                        double eps, const double* init7, orc_result* out, orc_trace* tr, int threads) {
+  threads = threads > 0 ? threads : 1;
+  double t0 = now_s();
+  struct Cls { std::vector<int32_t> orig; std::vector<float> xyz; std::vector<double> cov; KdTree tree; };
+  auto split = [&](const float* xyz, const uint32_t* lab, int n, std::vector<uint32_t>& order, std::map<uint32_t, Cls>& cls) {
+    for (int i = 0; i < n; i++) {
+      if (cls.find(lab[i]) == cls.end()) order.push_back(lab[i]);
+      Cls& c = cls[lab[i]];
+      c.orig.push_back(i); for (int d = 0; d < 3; d++) c.xyz.push_back(xyz[3 * (size_t)i + d]);
+    }
+    for (auto& kv : cls) {
+      Cls& c = kv.second; int m = (int)c.orig.size();
+      c.tree.build(c.xyz.data(), m); c.cov.resize(9 * (size_t)m);
+      covariances(c.xyz.data(), nullptr, m, c.tree, k, eps, 0, c.cov.data(), nullptr, nullptr, nullptr, threads);
+    }
+  };
+  std::vector<uint32_t> sorder, torder; std::map<uint32_t, Cls> scl, tcl;
+  split(sxyz, slab, ns, sorder, scl); split(txyz, tlab, nt, torder, tcl);
+  // flatten per-class storage so one Problem can index everything
+  std::vector<float> fs, ft; std::vector<double> cs, ct; std::map<uint32_t, int> soff, toff;
+  for (uint32_t l : sorder) { soff[l] = (int)(fs.size() / 3); fs.insert(fs.end(), scl[l].xyz.begin(), scl[l].xyz.end()); cs.insert(cs.end(), scl[l].cov.begin(), scl[l].cov.end()); }
+  for (uint32_t l : torder) { toff[l] = (int)(ft.size() / 3); ft.insert(ft.end(), tcl[l].xyz.begin(), tcl[l].xyz.end()); ct.insert(ct.end(), tcl[l].cov.begin(), tcl[l].cov.end()); }
+  SE3 cur = se3_from7(init7);
+  bool converged = false; size_t count = 0; int lm_total = 0; double fcost = 0; int ncorr = 0;
+  if (tr && tr->corr0) for (int i = 0; i < ns; i++) { tr->corr0[i] = -1; if (tr->w0) tr->w0[i] = 0; if (tr->d20) tr->d20[i] = INFINITY; }
+  while (!converged) {
+    SE3 est = cur;
+    count++;                                                       // semantic_icp.hpp:47
+    M3 R = quat_to_R(cur.q);
+    Problem P{fs.data(), cs.data(), ft.data(), ct.data(), {}, LOSS_SEMANTIC};
+    for (uint32_t s : sorder) {
+      if (tcl.find(s) == tcl.end()) continue;                      // :50
+      Cls& sc = scl[s]; Cls& tc = tcl[s];
+      int m = (int)sc.orig.size();
+      if (!(m > 400)) continue;                                    // :51
+      std::vector<int32_t> nn(m); std::vector<float> nd(m);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+      for (int i = 0; i < m; i++) {
+        float q[3]; transform_point(R, cur.t, &sc.xyz[3 * (size_t)i], q);
+        Cand c; int got = 0; tc.tree.knn(q, 1, &c, &got);
+        nn[i] = got ? c.i : -1; nd[i] = got ? c.d : INFINITY;
+      }
+      for (int i = 0; i < m; i++) {
+        bool g = nn[i] >= 0 && nd[i] < 250;                        // :69
+        if (g) P.res.push_back(Residual{soff[s] + i, toff[s] + nn[i], 1.0});
+        if (tr && count == 1 && tr->corr0) { tr->corr0[sc.orig[i]] = g ? tc.orig[nn[i]] : -1; if (tr->w0) tr->w0[sc.orig[i]] = g ? 1.0 : 0.0; if (tr->d20) tr->d20[sc.orig[i]] = nd[i]; }
+      }
+    }
+    LMStats st = lm_solve(P, &est, threads);
+    lm_total += st.iterations; fcost = st.final_cost; ncorr = (int)P.res.size();
+    double mse = sq_log_step(cur, est);
+    if (mse < 0.001 || count > 35) converged = true;               // :151-153
+    cur = est;
+    if (tr && (int)count - 1 < tr->max_passes) { size_t c0 = count - 1; se3_to7(cur, tr->pose7 + 7 * c0); tr->lm_iters[c0] = st.iterations; tr->n_res[c0] = ncorr; tr->cost[c0] = fcost; }
+  }
+  se3_to7(cur, out->pose7); out->outer_iter = (int)count; out->lm_iters_total = lm_total; out->final_cost = fcost; out->n_corr_last = ncorr;
+  out->seconds = now_s() - t0;
+}
+
+// per-class covariances in the original point order (for parity tests of the per-class precompute)
+void orc_covariances_per_class(const float* xyz, const uint32_t* lab, int n, int k, double eps, double* cov, double* normals, int threads) {
+  std::map<uint32_t, std::vector<int32_t>> mp;
+  for (int i = 0; i < n; i++) mp[lab[i]].push_back(i);
+  for (auto& kv : mp) {
+    int m = (int)kv.second.size();
+    std::vector<float> p(3 * (size_t)m);
+    for (int i = 0; i < m; i++) for (int d = 0; d < 3; d++) p[3 * (size_t)i + d] = xyz[3 * (size_t)kv.second[i] + d];
+    KdTree tree; tree.build(p.data(), m);
+    std::vector<double> c(9 * (size_t)m), nr(3 * (size_t)m);
+    covariances(p.data(), nullptr, m, tree, k, eps, 0, c.data(), nullptr, nr.data(), nullptr, threads > 0 ? threads : 1);
+    for (int i = 0; i < m; i++) {
+      std::memcpy(cov + 9 * (size_t)kv.second[i], &c[9 * (size_t)i], 9 * sizeof(double));
+      if (normals) std::memcpy(normals + 3 * (size_t)kv.second[i], &nr[3 * (size_t)i], 3 * sizeof(double));
+    }
+  }
+}
+
+}  // extern "C"
