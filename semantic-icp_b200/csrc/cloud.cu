@@ -1,0 +1,399 @@
+// cloud.cu — device-resident clouds: SoA upload, Morton sort, implicit 8-ary box tree over 32-point leaves.
+// Replaces the kd-tree construction of GICP::setSourceCloud/setTargetCloud (gicp.h:42-63),
+// EmIterativeClosestPoint::set*Cloud (em_icp.h:50-66) and pcl_2_semantic + addSemanticCloud
+// (pcl_2_semantic.h:14-42, impl/semantic_point_cloud.hpp:17-23).
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+#include "common.cuh"
+#include "knn.cuh"
+
+namespace sicp {
+
+static thread_local std::string g_err;
+static thread_local cudaStream_t g_stream = nullptr;
+void set_error(const std::string& msg) { g_err = msg; }
+cudaStream_t current_stream() { return g_stream; }
+
+// ---- bounding box: block reduce + ordered-int atomics -------------------------------------------------------
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void bbox_init_kernel(int* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = f2ord(INFINITY);
+  else if (threadIdx.x < 6) bb[threadIdx.x] = f2ord(-INFINITY);
+}
+__global__ void bbox_kernel(const float* __restrict__ xyz, int n, int* bb) {
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    for (int c = 0; c < 3; c++) {
+      float v = xyz[3 * (size_t)i + c];
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+  for (int c = 0; c < 3; c++) {
+    for (int o = 16; o; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&bb[c], f2ord(lo[c]));
+      atomicMax(&bb[3 + c], f2ord(hi[c]));
+    }
+  }
+}
+// writes the quantisation frame into every segment descriptor
+__global__ void frame_kernel(const int* bb, Segment* seg, int nseg) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  float lo[3], ext = 0.f;
+  for (int c = 0; c < 3; c++) {
+    lo[c] = ord2f(bb[c]);
+    ext = fmaxf(ext, ord2f(bb[3 + c]) - lo[c]);
+  }
+  if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
+  for (int c = 0; c < 3; c++) seg[s].lo[c] = lo[c];
+  seg[s].inv_cell = (float)((1u << kMortonBits) - 1) / ext;
+}
+__global__ void key_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rank, int n, const Segment* seg,
+                           uint64_t* keys, uint32_t* vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+  uint64_t k = morton57(x, y, z, seg[0].lo, seg[0].inv_cell);
+  if (rank) k |= (uint64_t)rank[i] << 57;
+  keys[i] = k;
+  vals[i] = (uint32_t)i;
+}
+// one thread per slot: gather the sorted point (or a NaN pad) and record the inverse permutation
+__global__ void slot_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sorted_idx,
+                            const uint64_t* __restrict__ sorted_keys, const int* __restrict__ seg_of_leaf, const Segment* __restrict__ seg,
+                            const int* __restrict__ seg_start, int nslots, float4* pts, uint32_t* label_out, int* slot_of_orig,
+                            uint64_t* leaf_code) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= nslots) return;
+  const int sid = seg_of_leaf[slot / kLeaf];
+  const int r = slot - seg[sid].p0;
+  float4 p = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(-1));
+  uint32_t lab = 0;
+  if (r < seg[sid].n) {
+    const int j = seg_start[sid] + r;
+    const uint32_t o = sorted_idx[j];
+    p = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2], __int_as_float((int)o));
+    if (labels) lab = labels[o];
+    slot_of_orig[o] = slot;
+    if ((slot & (kLeaf - 1)) == 0) leaf_code[slot / kLeaf] = sorted_keys[j] & kMortonMask;
+  }
+  pts[slot] = p;
+  label_out[slot] = lab;
+}
+// level 0: one warp per leaf
+__global__ void leaf_box_kernel(const float4* __restrict__ pts, const int* __restrict__ seg_of_leaf, const Segment* __restrict__ seg,
+                                int nleaf, float4* node_lo, float4* node_hi) {
+  const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  if (leaf >= nleaf) return;
+  const float4 p = pts[(size_t)leaf * kLeaf + (threadIdx.x & 31)];
+  float lo[3] = {p.x, p.y, p.z}, hi[3] = {p.x, p.y, p.z};
+  for (int c = 0; c < 3; c++)
+    for (int o = 16; o; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));  // fminf/fmaxf drop the NaN pads
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+  if ((threadIdx.x & 31) == 0) {
+    const Segment& sg = seg[seg_of_leaf[leaf]];
+    const int li = sg.node_off[0] + (leaf - sg.leaf0);
+    node_lo[li] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    node_hi[li] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  }
+}
+// upper levels: one block per segment, levels separated by __syncthreads
+__global__ void upper_box_kernel(const Segment* __restrict__ seg, float4* node_lo, float4* node_hi) {
+  const Segment sg = seg[blockIdx.x];
+  for (int l = 1; l < sg.nlevels; l++) {
+    for (int i = threadIdx.x; i < sg.node_cnt[l]; i += blockDim.x) {
+      const int c0 = i * kArity, c1 = min(c0 + kArity, sg.node_cnt[l - 1]);
+      float4 lo = node_lo[sg.node_off[l - 1] + c0], hi = node_hi[sg.node_off[l - 1] + c0];
+      for (int c = c0 + 1; c < c1; c++) {
+        const float4 a = node_lo[sg.node_off[l - 1] + c], b = node_hi[sg.node_off[l - 1] + c];
+        lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+        hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+      }
+      node_lo[sg.node_off[l] + i] = lo;
+      node_hi[sg.node_off[l] + i] = hi;
+    }
+    __syncthreads();
+  }
+}
+__global__ void pack_xyz_kernel(const float4* __restrict__ pts, int nslots, float* xyz_out) {  // slots -> original order
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  float4 p = pts[s];
+  int o = __float_as_int(p.w);
+  if (o >= 0) { xyz_out[3 * (size_t)o] = p.x; xyz_out[3 * (size_t)o + 1] = p.y; xyz_out[3 * (size_t)o + 2] = p.z; }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t* d_labels, const uint8_t* d_rank,
+                               const std::vector<int>& class_sizes, cudaStream_t st) {
+  const int n = (int)c->n;
+  const int nseg = (int)class_sizes.size();
+  c->nseg = nseg;
+  c->h_seg.assign(nseg, Segment());
+  std::vector<int> seg_start(nseg);
+  int p0 = 0, leaf0 = 0, node0 = 0, start = 0;
+  for (int s = 0; s < nseg; s++) {
+    Segment& sg = c->h_seg[s];
+    std::memset(&sg, 0, sizeof sg);
+    sg.p0 = p0; sg.n = class_sizes[s]; sg.nleaf = (sg.n + kLeaf - 1) / kLeaf; sg.leaf0 = leaf0;
+    sg.label = c->layout == SICP_CLOUD_PER_CLASS ? c->class_labels[s] : 0;
+    int cnt = sg.nleaf, l = 0;
+    for (;;) {
+      sg.node_off[l] = node0; sg.node_cnt[l] = cnt; node0 += cnt; l++;
+      if (cnt <= kArity || l >= kMaxLevels) break;
+      cnt = (cnt + kArity - 1) / kArity;
+    }
+    sg.nlevels = l;
+    seg_start[s] = start;
+    start += sg.n; p0 += sg.nleaf * kLeaf; leaf0 += sg.nleaf;
+  }
+  c->nslots = p0; c->nleaf = leaf0; c->nnodes = node0;
+  std::vector<int> seg_of_leaf(c->nleaf);
+  for (int s = 0; s < nseg; s++) std::fill(seg_of_leaf.begin() + c->h_seg[s].leaf0, seg_of_leaf.begin() + c->h_seg[s].leaf0 + c->h_seg[s].nleaf, s);
+
+  SICP_CUDA(cudaMallocAsync(&c->d_pts, sizeof(float4) * std::max(1, c->nslots), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_label, sizeof(uint32_t) * std::max(1, c->nslots), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_seg_of_leaf, sizeof(int) * std::max(1, c->nleaf), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_seg, sizeof(Segment) * std::max(1, nseg), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_node_lo, sizeof(float4) * std::max(1, c->nnodes), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_node_hi, sizeof(float4) * std::max(1, c->nnodes), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_leaf_code, sizeof(uint64_t) * std::max(1, c->nleaf), st));
+  SICP_CUDA(cudaMallocAsync(&c->d_slot_of_orig, sizeof(int) * std::max(1, n), st));
+  if (n == 0) return SICP_OK;
+
+  int* d_seg_start; int* d_bb; uint64_t *d_keys, *d_keys2; uint32_t *d_vals, *d_vals2; void* d_tmp = nullptr; size_t tmp_bytes = 0;
+  SICP_CUDA(cudaMallocAsync(&d_seg_start, sizeof(int) * nseg, st));
+  SICP_CUDA(cudaMallocAsync(&d_bb, sizeof(int) * 6, st));
+  SICP_CUDA(cudaMallocAsync(&d_keys, sizeof(uint64_t) * n, st));
+  SICP_CUDA(cudaMallocAsync(&d_keys2, sizeof(uint64_t) * n, st));
+  SICP_CUDA(cudaMallocAsync(&d_vals, sizeof(uint32_t) * n, st));
+  SICP_CUDA(cudaMallocAsync(&d_vals2, sizeof(uint32_t) * n, st));
+  // small host tables: the source vectors die at return, so these copies are synchronous w.r.t. the host
+  SICP_CUDA(cudaMemcpyAsync(c->d_seg, c->h_seg.data(), sizeof(Segment) * nseg, cudaMemcpyHostToDevice, st));
+  SICP_CUDA(cudaMemcpyAsync(c->d_seg_of_leaf, seg_of_leaf.data(), sizeof(int) * c->nleaf, cudaMemcpyHostToDevice, st));
+  SICP_CUDA(cudaMemcpyAsync(d_seg_start, seg_start.data(), sizeof(int) * nseg, cudaMemcpyHostToDevice, st));
+
+  const int T = 256;
+  bbox_init_kernel<<<1, 32, 0, st>>>(d_bb);
+  bbox_kernel<<<std::min((n + T - 1) / T, 296), T, 0, st>>>(d_xyz, n, d_bb);
+  frame_kernel<<<(nseg + 63) / 64, 64, 0, st>>>(d_bb, c->d_seg, nseg);
+  key_kernel<<<(n + T - 1) / T, T, 0, st>>>(d_xyz, d_rank, n, c->d_seg, d_keys, d_vals);
+  const int end_bit = d_rank ? 64 : 57;
+  SICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, end_bit, st));
+  SICP_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes, st));
+  SICP_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, end_bit, st));
+  slot_kernel<<<(c->nslots + T - 1) / T, T, 0, st>>>(d_xyz, d_labels, d_vals2, d_keys2, c->d_seg_of_leaf, c->d_seg, d_seg_start, c->nslots,
+                                                     c->d_pts, c->d_label, c->d_slot_of_orig, c->d_leaf_code);
+  leaf_box_kernel<<<(c->nleaf * 32 + T - 1) / T, T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_node_lo, c->d_node_hi);
+  upper_box_kernel<<<nseg, 256, 0, st>>>(c->d_seg, c->d_node_lo, c->d_node_hi);
+  SICP_CUDA(cudaGetLastError());
+  // frame (lo, inv_cell) back into the host copy is not needed: kernels read it from d_seg.
+  SICP_CUDA(cudaFreeAsync(d_tmp, st));
+  SICP_CUDA(cudaFreeAsync(d_vals2, st)); SICP_CUDA(cudaFreeAsync(d_vals, st));
+  SICP_CUDA(cudaFreeAsync(d_keys2, st)); SICP_CUDA(cudaFreeAsync(d_keys, st));
+  SICP_CUDA(cudaFreeAsync(d_bb, st)); SICP_CUDA(cudaFreeAsync(d_seg_start, st));
+  // seg_of_leaf / h_seg / seg_start are pageable host vectors: wait so they may go out of scope
+  SICP_CUDA(cudaStreamSynchronize(st));
+  return SICP_OK;
+}
+
+// first-appearance class order (pcl_2_semantic.h:24-35) → per-point rank + class sizes
+static sicp_status classify(sicp_cloud* c, const uint32_t* h_labels, size_t n, std::vector<uint8_t>* rank, std::vector<int>* sizes) {
+  std::unordered_map<uint32_t, int> idx;
+  rank->resize(n);
+  for (size_t i = 0; i < n; i++) {
+    auto it = idx.find(h_labels[i]);
+    int r;
+    if (it == idx.end()) {
+      r = (int)c->class_labels.size();
+      SICP_REQUIRE(r < 128, "PER_CLASS clouds support at most 128 distinct labels");
+      idx.emplace(h_labels[i], r);
+      c->class_labels.push_back(h_labels[i]);
+      sizes->push_back(0);
+    } else r = it->second;
+    (*rank)[i] = (uint8_t)r;
+    (*sizes)[r]++;
+  }
+  return SICP_OK;
+}
+
+static sicp_status init_device(int device) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
+    set_error("no CUDA device available (libsicp_b200 has no CPU fallback)");
+    return SICP_ERR_CUDA;
+  }
+  SICP_REQUIRE(device >= 0 && device < cnt, "device index out of range");
+  SICP_CUDA(cudaSetDevice(device));
+  cudaMemPool_t pool;
+  SICP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  SICP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));  // keep freed blocks cached
+  return SICP_OK;
+}
+
+}  // namespace sicp
+
+using namespace sicp;
+
+sicp::CloudView sicp_cloud::view() const {
+  CloudView v;
+  v.n = (int)n; v.nslots = nslots; v.nseg = nseg;
+  v.pts = d_pts; v.label = d_label; v.seg_of_leaf = d_seg_of_leaf; v.seg = d_seg;
+  v.node_lo = d_node_lo; v.node_hi = d_node_hi; v.leaf_code = d_leaf_code;
+  v.nrm = d_nrm; v.avec = d_avec; v.N = pre_N;
+  return v;
+}
+
+extern "C" {
+
+const char* sicp_last_error(void) { return g_err.c_str(); }
+const char* sicp_version(void) { return "sicp_b200 0.1 (sm_100a)"; }
+sicp_status sicp_device_count(int* count) {
+  SICP_REQUIRE(count, "count is null");
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+  *count = c;
+  return SICP_OK;
+}
+sicp_status sicp_set_stream(void* s) { g_stream = (cudaStream_t)s; return SICP_OK; }
+
+static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, const uint32_t* h_labels, size_t n, int layout,
+                                 int device, sicp_cloud** out) {
+  cudaStream_t st = current_stream();
+  sicp_cloud* c = new sicp_cloud();
+  c->device = device; c->layout = layout; c->n = n; c->has_labels = d_labels != nullptr;
+  std::vector<int> sizes;
+  uint8_t* d_rank = nullptr;
+  sicp_status rc = SICP_OK;
+  if (layout == SICP_CLOUD_PER_CLASS) {
+    std::vector<uint8_t> rank;
+    rc = classify(c, h_labels, n, &rank, &sizes);
+    if (rc == SICP_OK && n > 0) {
+      if (cudaMallocAsync(&d_rank, n, st) != cudaSuccess || cudaMemcpyAsync(d_rank, rank.data(), n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) { set_error("rank upload failed"); rc = SICP_ERR_CUDA; }
+    }
+  } else sizes.push_back((int)n);
+  if (rc == SICP_OK) rc = build_cloud(c, d_xyz, d_labels, d_rank, sizes, st);
+  if (d_rank) cudaFreeAsync(d_rank, st);
+  if (rc != SICP_OK) { sicp_cloud_destroy(c); return rc; }
+  *out = c;
+  return SICP_OK;
+}
+
+sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* labels, size_t label_stride, size_t n, int layout,
+                              int device, sicp_cloud** out) {
+  SICP_REQUIRE(out, "out is null");
+  SICP_REQUIRE(xyz || n == 0, "xyz is null");
+  SICP_REQUIRE(xyz_stride >= 12 && (labels == nullptr || label_stride >= 4), "stride too small");
+  SICP_REQUIRE(n < (1u << 30), "too many points");
+  SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || layout == SICP_CLOUD_PER_CLASS, "bad layout");
+  SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || labels, "PER_CLASS layout needs labels");
+  SICP_CHECK(init_device(device));
+  cudaStream_t st = current_stream();
+  float* d_xyz = nullptr; uint32_t* d_lab = nullptr;
+  std::vector<uint32_t> h_lab;
+  SICP_CUDA(cudaMallocAsync(&d_xyz, std::max<size_t>(1, n) * 12, st));
+  if (n) SICP_CUDA(cudaMemcpy2DAsync(d_xyz, 12, xyz, xyz_stride, 12, n, cudaMemcpyHostToDevice, st));
+  if (labels) {
+    SICP_CUDA(cudaMallocAsync(&d_lab, std::max<size_t>(1, n) * 4, st));
+    if (n) SICP_CUDA(cudaMemcpy2DAsync(d_lab, 4, labels, label_stride, 4, n, cudaMemcpyHostToDevice, st));
+    if (layout == SICP_CLOUD_PER_CLASS) {
+      h_lab.resize(n);
+      for (size_t i = 0; i < n; i++) std::memcpy(&h_lab[i], (const char*)labels + i * label_stride, 4);
+    }
+  }
+  sicp_status rc = create_common(d_xyz, d_lab, h_lab.data(), n, layout, device, out);
+  cudaFreeAsync(d_xyz, st);
+  if (d_lab) cudaFreeAsync(d_lab, st);
+  return rc;
+}
+
+sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_labels, size_t n, int layout, int device, sicp_cloud** out) {
+  SICP_REQUIRE(out, "out is null");
+  SICP_REQUIRE(d_xyz || n == 0, "d_xyz is null");
+  SICP_REQUIRE(n < (1u << 30), "too many points");
+  SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || layout == SICP_CLOUD_PER_CLASS, "bad layout");
+  SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || d_labels, "PER_CLASS layout needs labels");
+  SICP_CHECK(init_device(device));
+  std::vector<uint32_t> h_lab;
+  if (layout == SICP_CLOUD_PER_CLASS && n) {
+    h_lab.resize(n);
+    SICP_CUDA(cudaMemcpyAsync(h_lab.data(), d_labels, n * 4, cudaMemcpyDeviceToHost, current_stream()));
+    SICP_CUDA(cudaStreamSynchronize(current_stream()));
+  }
+  return create_common(d_xyz, d_labels, h_lab.data(), n, layout, device, out);
+}
+
+void sicp_cloud_destroy(sicp_cloud* c) {
+  if (!c) return;
+  cudaStream_t st = current_stream();
+  cudaSetDevice(c->device);
+  void* bufs[] = {c->d_pts, c->d_label, c->d_seg_of_leaf, c->d_seg, c->d_node_lo, c->d_node_hi, c->d_leaf_code, c->d_slot_of_orig,
+                  c->d_nrm, c->d_avec, c->d_dist, c->d_selfnn};
+  for (void* b : bufs) if (b) cudaFreeAsync(b, st);
+  delete c;
+}
+
+sicp_status sicp_cloud_size(const sicp_cloud* c, size_t* n) {
+  SICP_REQUIRE(c && n, "null argument");
+  *n = c->n;
+  return SICP_OK;
+}
+
+sicp_status sicp_cloud_get_classes(const sicp_cloud* c, uint32_t* labels_out, int32_t* sizes_out, int* n_inout) {
+  SICP_REQUIRE(c && n_inout, "null argument");
+  SICP_REQUIRE(c->layout == SICP_CLOUD_PER_CLASS, "cloud is not PER_CLASS");
+  int cap = *n_inout;
+  *n_inout = c->nseg;
+  for (int s = 0; s < c->nseg && s < cap; s++) {
+    if (labels_out) labels_out[s] = c->class_labels[s];
+    if (sizes_out) sizes_out[s] = c->h_seg[s].n;
+  }
+  return SICP_OK;
+}
+
+sicp_status sicp_cloud_transform_f32(const sicp_cloud* c, const double* pose7, void* out_xyz, size_t out_stride) {
+  // Matrix4f path of the finalisation (gicp.hpp:166-171): float matrix, float math, host-side (n*12 B; not on the hot path
+  // of the pose).  The device holds the points in sorted order; fetch them back in original order first.
+  SICP_REQUIRE(c && pose7 && out_xyz && out_stride >= 12, "bad argument");
+  cudaStream_t st = current_stream();
+  SICP_CUDA(cudaSetDevice(c->device));
+  std::vector<float> h(3 * c->n);
+  float* d_tmp;
+  SICP_CUDA(cudaMallocAsync(&d_tmp, std::max<size_t>(1, c->n) * 12, st));
+  if (c->nslots) pack_xyz_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->d_pts, c->nslots, d_tmp);
+  SICP_CUDA(cudaMemcpyAsync(h.data(), d_tmp, c->n * 12, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaStreamSynchronize(st));
+  SICP_CUDA(cudaFreeAsync(d_tmp, st));
+  double Rd[9];
+  {
+    const double x = pose7[0], y = pose7[1], z = pose7[2], w = pose7[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x,
+                 tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    Rd[0] = 1 - (tyy + tzz); Rd[1] = txy - twz; Rd[2] = txz + twy; Rd[3] = txy + twz; Rd[4] = 1 - (txx + tzz); Rd[5] = tyz - twx;
+    Rd[6] = txz - twy; Rd[7] = tyz + twx; Rd[8] = 1 - (txx + tyy);
+  }
+  float M[12];
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) M[4 * i + j] = (float)Rd[3 * i + j]; M[4 * i + 3] = (float)pose7[4 + i]; }
+  for (size_t i = 0; i < c->n; i++) {
+    const float x = h[3 * i], y = h[3 * i + 1], z = h[3 * i + 2];
+    float o[3];
+    for (int r = 0; r < 3; r++) o[r] = M[4 * r] * x + M[4 * r + 1] * y + M[4 * r + 2] * z + M[4 * r + 3];
+    std::memcpy((char*)out_xyz + i * out_stride, o, 12);
+  }
+  return SICP_OK;
+}
+
+}  // extern "C"

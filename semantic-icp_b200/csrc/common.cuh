@@ -1,0 +1,105 @@
+// common.cuh — shared host/device definitions of libsicp_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "sicp_b200.h"
+
+namespace sicp {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const std::string& msg);
+#define SICP_CUDA(call)                                                                                   \
+  do {                                                                                                    \
+    cudaError_t _e = (call);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      ::sicp::set_error(std::string(#call) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ ":" +   \
+                        std::to_string(__LINE__) + ")");                                                  \
+      return SICP_ERR_CUDA;                                                                               \
+    }                                                                                                     \
+  } while (0)
+#define SICP_CHECK(st)                     \
+  do {                                     \
+    sicp_status _s = (st);                 \
+    if (_s != SICP_OK) return _s;          \
+  } while (0)
+#define SICP_REQUIRE(cond, msg)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::sicp::set_error(msg);              \
+      return SICP_ERR_INVALID;             \
+    }                                      \
+  } while (0)
+
+cudaStream_t current_stream();
+
+// ------------------------------------------------------------------ search structure
+constexpr int kLeaf = 32;        // points per leaf == warp size: one warp owns one leaf of queries
+constexpr int kArity = 8;        // children per internal node
+constexpr int kMaxLevels = 10;   // 32 * 8^9 points
+constexpr int kMaxClasses = 64;  // label vectors live in registers of two lanes-worth (N <= 64)
+constexpr int kMaxK = 32;
+
+// One searchable point set: the whole cloud, or one semantic class (SemanticPointCloud::labeledKdTrees).
+struct Segment {
+  int p0;                      // first slot in the sorted arrays (multiple of kLeaf)
+  int n;                       // real points
+  int nleaf;                   // ceil(n / kLeaf)
+  int nlevels;                 // levels in the implicit tree; level 0 = leaves
+  int node_off[kMaxLevels];    // offset of each level in the node arrays
+  int node_cnt[kMaxLevels];
+  int leaf0;                   // index of this segment's first leaf in leaf_code[]
+  uint32_t label;              // class label (PER_CLASS) or 0
+  float lo[3];                 // Morton quantisation frame
+  float inv_cell;
+};
+
+// Device view of a cloud, passed to kernels by value.
+struct CloudView {
+  int n;                 // real points
+  int nslots;            // padded slots (multiple of kLeaf per segment)
+  int nseg;
+  const float4* pts;     // [nslots] sorted: x,y,z, original index bits (pad: NaN, -1)
+  const uint32_t* label; // [nslots] sorted labels (0 if none)
+  const int* seg_of_leaf;// [nleaf_total] segment id of each leaf (== of each query warp)
+  const Segment* seg;    // [nseg]
+  const float4* node_lo; // node boxes, all segments / levels
+  const float4* node_hi;
+  const uint64_t* leaf_code;  // [nleaf_total] Morton code of the first point of each leaf
+  const double* nrm;     // [3*nslots] SoA normals nx | ny | nz  (after precompute)
+  const double* avec;    // [nslots*N] label vectors a_p = CM^T dist_p (EM)
+  int N;
+};
+
+}  // namespace sicp
+
+struct sicp_cloud {
+  int device = 0;
+  int layout = 0;
+  size_t n = 0;
+  int nslots = 0, nseg = 0, nleaf = 0, nnodes = 0;
+  std::vector<sicp::Segment> h_seg;
+  std::vector<uint32_t> class_labels;  // first-appearance order
+  // device buffers
+  float4* d_pts = nullptr;
+  uint32_t* d_label = nullptr;
+  int* d_seg_of_leaf = nullptr;
+  sicp::Segment* d_seg = nullptr;
+  float4* d_node_lo = nullptr;
+  float4* d_node_hi = nullptr;
+  uint64_t* d_leaf_code = nullptr;
+  int* d_slot_of_orig = nullptr;  // [n] inverse permutation
+  double* d_nrm = nullptr;
+  double* d_avec = nullptr;
+  double* d_dist = nullptr;       // [nslots*N] raw label distributions (kept for parity tests)
+  int* d_selfnn = nullptr;        // [nslots*k] self neighbours (slots)
+  // precompute cache key
+  bool pre_valid = false;
+  int pre_k = 0, pre_N = 0;
+  double pre_eps = 0;
+  std::vector<double> pre_cm;
+  bool has_labels = false;
+  uint32_t max_label = 0;
+  sicp::CloudView view() const;
+};

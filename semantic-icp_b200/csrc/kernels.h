@@ -1,0 +1,53 @@
+// kernels.h — host-side launchers shared between the translation units of libsicp_b200.
+#pragma once
+#include "common.cuh"
+
+namespace sicp {
+
+// Device-resident control block of one registration: the outer ICP loop state lives here so that passes can be
+// enqueued back to back without a host round trip (kernels return immediately once `converged` is set).
+struct RegCtl {
+  double pose[7];        // current transform (source -> target)
+  int converged;         // set by the LM kernel's epilogue (impl/gicp.hpp:153-155 etc.)
+  int outer;             // passes completed
+  int lm_iters_total;
+  int lm_evals_total;
+  int n_corr_last;
+  int term_last;
+  int flags;
+  int n_corr_pass;
+  double final_cost;
+  double last_mse;
+  double pass_pose[64][7];
+  int pass_lm_iters[64];
+};
+
+struct LMConfig {
+  int algo;              // SICP_ALGO_*
+  int kc;                // correspondences per source point
+  double eps;            // PCA epsilon
+  int max_iter;          // 400
+  double mse_stop;       // 1e-5 (GICP, EM) / 1e-3 (SEMANTIC)
+  int outer_cap;         // 50 / 35
+};
+
+sicp_status launch_self_knn_pca(const sicp_cloud* c, int k, double* d_nrm, int* d_selfnn, uint8_t* d_nbr_label, cudaStream_t st);
+sicp_status launch_cross_knn(const sicp_cloud* src, const sicp_cloud* tgt, const double* d_pose7, const int* d_stop, const int* d_tseg_of_sseg,
+                             int kc, int* d_corr, float* d_d2, cudaStream_t st);
+sicp_status make_class_map(const sicp_cloud* src, const sicp_cloud* tgt, int min_src_points, int** d_map_out, cudaStream_t st);
+
+// E-step: gate + label-compatibility weight + probability gate (impl/em_icp.hpp:65-89,108; gicp_cost_function.h:75-87)
+sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, double gate_d2, const double* d_pose7,
+                         const int* d_stop, int* d_corr, const float* d_d2, double* d_w, RegCtl* d_ctl, cudaStream_t st);
+// M-step: one inner solve (ceres::Solve at impl/gicp.hpp:149-151) + outer-loop bookkeeping, cooperative kernel
+int lm_grid_blocks(int device);
+sicp_status launch_lm(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, const int* d_corr, const double* d_w, RegCtl* d_ctl,
+                      double* d_partials, int grid, cudaStream_t st);
+// Single evaluation (cost, g, H) at a given pose, for parity tests
+sicp_status launch_evaluate(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, const int* d_corr, const double* d_w,
+                            const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st);
+// fused labels (impl/em_icp.hpp:202-268)
+sicp_status launch_fused_labels(const sicp_cloud* src, const sicp_cloud* tgt, double eps, double gate_d2, const double* d_pose7, const int* d_corr,
+                                const float* d_d2, uint32_t* d_labels_out, cudaStream_t st);
+
+}  // namespace sicp

@@ -1,0 +1,371 @@
+// register.cu — host orchestration of one align(): covariance precompute, then outer passes
+// [transform + kNN] -> [E-step] -> [cooperative LM solve + convergence test], all control state device-resident.
+// Replaces the bodies of GICP::align (impl/gicp.hpp:29-175), SemanticIterativeClosestPoint::align
+// (impl/semantic_icp.hpp:27-166) and EmIterativeClosestPoint::align (impl/em_icp.hpp:24-200).
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sicp {
+
+static LMConfig make_cfg(int algo, const sicp_options& o) {
+  LMConfig c;
+  c.algo = algo;
+  c.kc = algo == SICP_ALGO_EM ? 4 : 1;                      // em_icp.hpp:60 / gicp.hpp:69, semantic_icp.hpp:68
+  c.eps = o.epsilon;
+  c.max_iter = o.max_lm_iterations;
+  c.mse_stop = algo == SICP_ALGO_SEMANTIC ? 1e-3 : 1e-5;    // semantic_icp.hpp:152 / gicp.hpp:154, em_icp.hpp:180
+  c.outer_cap = algo == SICP_ALGO_SEMANTIC ? 35 : 50;
+  return c;
+}
+
+static sicp_status validate(int algo, const sicp_cloud* src, const sicp_cloud* tgt, const sicp_options* o) {
+  SICP_REQUIRE(src && tgt && o, "null argument");
+  SICP_REQUIRE(algo == SICP_ALGO_GICP || algo == SICP_ALGO_SEMANTIC || algo == SICP_ALGO_EM, "unknown algorithm");
+  SICP_REQUIRE(src->device == tgt->device, "clouds live on different devices");
+  if (algo == SICP_ALGO_SEMANTIC) SICP_REQUIRE(src->layout == SICP_CLOUD_PER_CLASS && tgt->layout == SICP_CLOUD_PER_CLASS, "SEMANTIC needs PER_CLASS clouds");
+  else SICP_REQUIRE(src->layout == SICP_CLOUD_WHOLE && tgt->layout == SICP_CLOUD_WHOLE, "GICP/EM need WHOLE clouds");
+  if (algo == SICP_ALGO_EM) {
+    SICP_REQUIRE(o->n_classes >= 1 && o->n_classes <= kMaxClasses && o->confusion, "EM needs n_classes in 1..64 and a confusion matrix");
+    SICP_REQUIRE(src->has_labels && tgt->has_labels, "EM needs labelled clouds");
+  }
+  SICP_REQUIRE(o->k_cov >= 1 && o->k_cov <= kMaxK, "k_cov must be in 1..32");
+  return SICP_OK;
+}
+
+static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* o) {
+  const int N = algo == SICP_ALGO_EM ? o->n_classes : 0;
+  SICP_CHECK(sicp_cloud_precompute(src, o->k_cov, o->epsilon, N, o->confusion));
+  if (tgt != src) SICP_CHECK(sicp_cloud_precompute(tgt, o->k_cov, o->epsilon, N, o->confusion));
+  return SICP_OK;
+}
+
+// Pinned control blocks are pooled: cudaMallocHost / cudaFreeHost synchronise the device and would serialise
+// concurrent registrations.
+static std::mutex g_pin_mu;
+static std::vector<RegCtl*> g_pin_free;
+static RegCtl* pin_get() {
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    if (!g_pin_free.empty()) { RegCtl* p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
+  }
+  RegCtl* p = nullptr;
+  if (cudaMallocHost(&p, sizeof(RegCtl)) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pin_put(RegCtl* p) { std::lock_guard<std::mutex> lk(g_pin_mu); g_pin_free.push_back(p); }
+
+// Per-registration device workspace
+struct Workspace {
+  int* d_corr = nullptr; float* d_d2 = nullptr; double* d_w = nullptr; RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
+  RegCtl* h_ctl = nullptr;  // pinned
+  int grid = 0;
+  cudaStream_t st = nullptr;
+  sicp_status alloc(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, int min_class_points, cudaStream_t s) {
+    st = s;
+    const size_t nc = (size_t)std::max(1, src->nslots) * cfg.kc;
+    grid = lm_grid_blocks(src->device);
+    SICP_CUDA(cudaMallocAsync(&d_corr, sizeof(int) * nc, st));
+    SICP_CUDA(cudaMallocAsync(&d_d2, sizeof(float) * nc, st));
+    SICP_CUDA(cudaMallocAsync(&d_w, sizeof(double) * nc, st));
+    SICP_CUDA(cudaMallocAsync(&d_ctl, sizeof(RegCtl), st));
+    SICP_CUDA(cudaMallocAsync(&d_partials, sizeof(double) * 2 * 28 * grid, st));
+    h_ctl = pin_get();
+    if (!h_ctl) { set_error("pinned allocation failed"); return SICP_ERR_CUDA; }
+    if (cfg.algo == SICP_ALGO_SEMANTIC) SICP_CHECK(make_class_map(src, tgt, min_class_points, &d_map, st));
+    return SICP_OK;
+  }
+  void release() {
+    if (d_corr) cudaFreeAsync(d_corr, st);
+    if (d_d2) cudaFreeAsync(d_d2, st);
+    if (d_w) cudaFreeAsync(d_w, st);
+    if (d_ctl) cudaFreeAsync(d_ctl, st);
+    if (d_partials) cudaFreeAsync(d_partials, st);
+    if (d_map) cudaFreeAsync(d_map, st);
+    if (h_ctl) pin_put(h_ctl);
+    *this = Workspace();
+  }
+};
+
+struct StageTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<int> stage;
+  void begin(int s, cudaStream_t st) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); stage.push_back(s); }
+  void end(cudaStream_t st) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); }
+  void collect(sicp_result* out) {
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) { out->stage_ms[stage[i / 2]] += ms; out->stage_launches[stage[i / 2]]++; }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear(); stage.clear();
+  }
+};
+
+// One registration as a resumable state machine so that several can be interleaved on different streams.
+struct Job {
+  int algo; sicp_cloud* src; sicp_cloud* tgt; const sicp_options* opts; LMConfig cfg; Workspace ws; StageTimer tm;
+  sicp_result* out; int enqueued = 0; bool finished = false; int launches = 0;
+
+  sicp_status start(const double* init7, cudaStream_t st) {
+    std::memset(out, 0, sizeof *out);
+    cfg = make_cfg(algo, *opts);
+    tm.on = opts->profile != 0;
+    SICP_CHECK(ws.alloc(src, tgt, cfg, opts->min_class_points, st));
+    std::memset(ws.h_ctl, 0, sizeof(RegCtl));
+    std::memcpy(ws.h_ctl->pose, init7, 56);
+    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+    return SICP_OK;
+  }
+  sicp_status enqueue_pass() {
+    cudaStream_t st = ws.st;
+    const int* stop = &ws.d_ctl->converged;
+    tm.begin(SICP_STAGE_KNN, st);
+    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, stop, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
+    tm.end(st);
+    tm.begin(SICP_STAGE_ESTEP, st);
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, stop, ws.d_corr, ws.d_d2, ws.d_w, ws.d_ctl, st));
+    tm.end(st);
+    tm.begin(SICP_STAGE_LM, st);
+    SICP_CHECK(launch_lm(src, tgt, cfg, ws.d_corr, ws.d_w, ws.d_ctl, ws.d_partials, ws.grid, st));
+    tm.end(st);
+    launches += 3;
+    enqueued++;
+    return SICP_OK;
+  }
+  // enqueue a chunk of passes, then the control-block readback
+  sicp_status enqueue_chunk(int n) {
+    const int cap = cfg.outer_cap + 2;
+    for (int i = 0; i < n && enqueued < cap; i++) SICP_CHECK(enqueue_pass());
+    SICP_CUDA(cudaMemcpyAsync(ws.h_ctl, ws.d_ctl, sizeof(RegCtl), cudaMemcpyDeviceToHost, ws.st));
+    return SICP_OK;
+  }
+  // after the stream is synchronised: true when the registration is complete
+  bool done_after_sync() const { return ws.h_ctl->converged != 0 || enqueued >= cfg.outer_cap + 2; }
+  void finish() {
+    const RegCtl& c = *ws.h_ctl;
+    std::memcpy(out->pose7, c.pose, 56);
+    out->outer_iter = c.outer; out->lm_iters_total = c.lm_iters_total; out->final_cost = c.final_cost; out->n_corr_last = c.n_corr_last;
+    out->flags = c.flags; out->lm_evals_total = c.lm_evals_total;
+    const int np = std::min(c.outer, 64);
+    std::memcpy(out->pass_pose7, c.pass_pose, sizeof(double) * 7 * np);
+    std::memcpy(out->pass_lm_iters, c.pass_lm_iters, sizeof(int) * np);
+    out->gpu_launches = c.outer * 3;  // kernels that did work (passes enqueued past convergence return immediately)
+    tm.collect(out);
+    ws.release();
+    finished = true;
+  }
+};
+
+static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int max_concurrent) {
+  cudaStream_t base = current_stream();
+  const int nj = (int)jobs.size();
+  const int S = std::max(1, std::min(max_concurrent, nj));
+  std::vector<cudaStream_t> streams(S, base);
+  cudaEvent_t fork = nullptr;
+  if (S > 1) {
+    SICP_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    SICP_CUDA(cudaEventRecord(fork, base));
+    for (int s = 0; s < S; s++) {
+      SICP_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
+      SICP_CUDA(cudaStreamWaitEvent(streams[s], fork, 0));
+    }
+  }
+  sicp_status rc = SICP_OK;
+  const int kChunk = 3;
+  for (int j0 = 0; j0 < nj && rc == SICP_OK; j0 += S) {
+    const int j1 = std::min(nj, j0 + S);
+    for (int j = j0; j < j1 && rc == SICP_OK; j++) {
+      rc = jobs[j].start(init7s + 7 * (size_t)j, streams[j - j0]);
+      if (rc == SICP_OK) rc = jobs[j].enqueue_chunk(kChunk);
+    }
+    int live = j1 - j0;
+    while (live > 0 && rc == SICP_OK) {
+      for (int j = j0; j < j1 && rc == SICP_OK; j++) {
+        if (jobs[j].finished) continue;
+        if (cudaStreamSynchronize(jobs[j].ws.st) != cudaSuccess) { set_error(std::string("stream sync failed: ") + cudaGetErrorString(cudaGetLastError())); rc = SICP_ERR_CUDA; break; }
+        if (jobs[j].done_after_sync()) { jobs[j].finish(); live--; }
+        else rc = jobs[j].enqueue_chunk(kChunk);
+      }
+    }
+  }
+  for (Job& jb : jobs) if (!jb.finished) jb.ws.release();
+  if (S > 1) {
+    for (int s = 0; s < S; s++) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      cudaEventRecord(e, streams[s]);
+      cudaStreamWaitEvent(base, e, 0);
+      cudaEventDestroy(e);
+      cudaStreamDestroy(streams[s]);
+    }
+    cudaEventDestroy(fork);
+  }
+  return rc;
+}
+
+}  // namespace sicp
+
+using namespace sicp;
+
+extern "C" {
+
+void sicp_options_default(int algo, sicp_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof *o);
+  o->k_cov = 20;            // gicp.h:34, em_icp.h:42, semantic_point_cloud.h:31
+  o->epsilon = 0.001;
+  o->gate_d2 = 250.0;       // gicp.hpp:70
+  o->min_class_points = 400;  // semantic_icp.hpp:51
+  o->max_lm_iterations = 400; // gicp.hpp:143
+  (void)algo;
+}
+
+sicp_status sicp_register(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* init7, sicp_result* out) {
+  SICP_REQUIRE(init7 && out, "null argument");
+  SICP_CHECK(validate(algo, src, tgt, opts));
+  SICP_CUDA(cudaSetDevice(src->device));
+  cudaStream_t st = current_stream();
+  StageTimer pre;
+  pre.on = opts->profile != 0;
+  pre.begin(SICP_STAGE_COV, st);
+  SICP_CHECK(precompute_pair(algo, src, tgt, opts));
+  pre.end(st);
+  std::vector<Job> jobs(1);
+  jobs[0].algo = algo; jobs[0].src = src; jobs[0].tgt = tgt; jobs[0].opts = opts; jobs[0].out = out;
+  sicp_status rc = run_jobs(jobs, init7, 1);
+  if (rc == SICP_OK) pre.collect(out);
+  return rc;
+}
+
+sicp_status sicp_register_batch(int algo, size_t n_pairs, sicp_cloud* const* src, sicp_cloud* const* tgt, const sicp_options* opts,
+                                const double* init7s, sicp_result* out) {
+  SICP_REQUIRE(src && tgt && init7s && out, "null argument");
+  if (n_pairs == 0) return SICP_OK;
+  for (size_t i = 0; i < n_pairs; i++) {
+    SICP_CHECK(validate(algo, src[i], tgt[i], opts));
+    SICP_REQUIRE(src[i]->device == src[0]->device, "all pairs of a batch must live on one device");
+  }
+  SICP_CUDA(cudaSetDevice(src[0]->device));
+  for (size_t i = 0; i < n_pairs; i++) SICP_CHECK(precompute_pair(algo, src[i], tgt[i], opts));
+  std::vector<Job> jobs(n_pairs);
+  for (size_t i = 0; i < n_pairs; i++) { jobs[i].algo = algo; jobs[i].src = src[i]; jobs[i].tgt = tgt[i]; jobs[i].opts = opts; jobs[i].out = out + i; }
+  return run_jobs(jobs, init7s, 8);
+}
+
+sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* pose7, int32_t* idx_out,
+                                 double* w_out, float* d2_out) {
+  SICP_REQUIRE(pose7 && idx_out, "null argument");
+  SICP_CHECK(validate(algo, src, tgt, opts));
+  SICP_CUDA(cudaSetDevice(src->device));
+  SICP_CHECK(precompute_pair(algo, src, tgt, opts));
+  cudaStream_t st = current_stream();
+  LMConfig cfg = make_cfg(algo, *opts);
+  Workspace ws;
+  sicp_status rc = ws.alloc(src, tgt, cfg, opts->min_class_points, st);
+  if (rc != SICP_OK) { ws.release(); return rc; }
+  std::memset(ws.h_ctl, 0, sizeof(RegCtl));
+  std::memcpy(ws.h_ctl->pose, pose7, 56);
+  const size_t nslot_c = (size_t)src->nslots * cfg.kc, n_c = src->n * cfg.kc;
+  std::vector<int> h_corr(nslot_c); std::vector<float> h_d2(nslot_c); std::vector<double> h_w(nslot_c);
+  std::vector<float4> h_spts(src->nslots), h_tpts(tgt->nslots);
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, nullptr, st));
+    SICP_CUDA(cudaMemcpyAsync(h_corr.data(), ws.d_corr, sizeof(int) * nslot_c, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaMemcpyAsync(h_d2.data(), ws.d_d2, sizeof(float) * nslot_c, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaMemcpyAsync(h_w.data(), ws.d_w, sizeof(double) * nslot_c, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaMemcpyAsync(h_spts.data(), src->d_pts, sizeof(float4) * src->nslots, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaMemcpyAsync(h_tpts.data(), tgt->d_pts, sizeof(float4) * tgt->nslots, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    return SICP_OK;
+  };
+  rc = body();
+  ws.release();
+  SICP_CHECK(rc);
+  (void)n_c;
+  for (int s = 0; s < src->nslots; s++) {
+    int o; std::memcpy(&o, &h_spts[s].w, 4);
+    if (o < 0) continue;
+    for (int c = 0; c < cfg.kc; c++) {
+      const int ts = h_corr[(size_t)s * cfg.kc + c];
+      int to = -1;
+      if (ts >= 0) std::memcpy(&to, &h_tpts[ts].w, 4);
+      idx_out[(size_t)o * cfg.kc + c] = to;
+      if (w_out) w_out[(size_t)o * cfg.kc + c] = h_w[(size_t)s * cfg.kc + c];
+      if (d2_out) d2_out[(size_t)o * cfg.kc + c] = h_d2[(size_t)s * cfg.kc + c];
+    }
+  }
+  return SICP_OK;
+}
+
+sicp_status sicp_evaluate(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* corr_pose7,
+                          const double* eval_pose7, double* cost, double* g6, double* H36) {
+  SICP_REQUIRE(corr_pose7 && eval_pose7 && cost && g6 && H36, "null argument");
+  SICP_CHECK(validate(algo, src, tgt, opts));
+  SICP_CUDA(cudaSetDevice(src->device));
+  SICP_CHECK(precompute_pair(algo, src, tgt, opts));
+  cudaStream_t st = current_stream();
+  LMConfig cfg = make_cfg(algo, *opts);
+  Workspace ws;
+  sicp_status rc = ws.alloc(src, tgt, cfg, opts->min_class_points, st);
+  if (rc != SICP_OK) { ws.release(); return rc; }
+  std::memset(ws.h_ctl, 0, sizeof(RegCtl));
+  std::memcpy(ws.h_ctl->pose, corr_pose7, 56);
+  std::memcpy(ws.h_ctl->pass_pose[0], eval_pose7, 56);  // scratch slot for the evaluation pose
+  double h_out[28];
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, nullptr, st));
+    double* d_out = &ws.d_ctl->pass_pose[8][0];
+    SICP_CHECK(launch_evaluate(src, tgt, cfg, ws.d_corr, ws.d_w, &ws.d_ctl->pass_pose[0][0], d_out, ws.d_partials, ws.grid, st));
+    SICP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    return SICP_OK;
+  };
+  rc = body();
+  ws.release();
+  SICP_CHECK(rc);
+  *cost = h_out[27];
+  for (int a = 0; a < 6; a++) {
+    g6[a] = h_out[21 + a];
+    for (int b = 0; b < 6; b++) { const int hi = std::max(a, b), lo = std::min(a, b); H36[6 * a + b] = h_out[hi * (hi + 1) / 2 + lo]; }
+  }
+  return SICP_OK;
+}
+
+sicp_status sicp_fused_labels(sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* pose7, uint32_t* labels_out) {
+  SICP_REQUIRE(pose7 && labels_out, "null argument");
+  SICP_CHECK(validate(SICP_ALGO_EM, src, tgt, opts));
+  SICP_CUDA(cudaSetDevice(src->device));
+  SICP_CHECK(precompute_pair(SICP_ALGO_EM, src, tgt, opts));
+  cudaStream_t st = current_stream();
+  LMConfig cfg = make_cfg(SICP_ALGO_EM, *opts);
+  Workspace ws;
+  sicp_status rc = ws.alloc(src, tgt, cfg, 0, st);
+  if (rc != SICP_OK) { ws.release(); return rc; }
+  std::memset(ws.h_ctl, 0, sizeof(RegCtl));
+  std::memcpy(ws.h_ctl->pose, pose7, 56);
+  uint32_t* d_lab = nullptr;
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMallocAsync(&d_lab, sizeof(uint32_t) * std::max<size_t>(1, src->n), st));
+    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, nullptr, 4, ws.d_corr, ws.d_d2, st));
+    SICP_CHECK(launch_fused_labels(src, tgt, opts->epsilon, opts->gate_d2, ws.d_ctl->pose, ws.d_corr, ws.d_d2, d_lab, st));
+    SICP_CUDA(cudaMemcpyAsync(labels_out, d_lab, sizeof(uint32_t) * src->n, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    return SICP_OK;
+  };
+  rc = body();
+  if (d_lab) cudaFreeAsync(d_lab, st);
+  ws.release();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): correspondence index sets bit-exact (exact NN, (d2_f32, index) ordering, same FP32
+distance arithmetic); poses within 1e-5 rad / 1e-4 m; f64 per-point quantities (normals, label vectors) bit-exact or
+<= 1e-12; reduced quantities (cost, gradient, J^T J) <= 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL, TRANS_TOL = 1e-5, 1e-4  # rad, m — north_star pose tolerance
+
+
+@pytest.fixture(scope="module")
+def room(pkg):
+    return pkg.synth.room_pair(seed=100, n_points=10_000)
+
+
+@pytest.fixture(scope="module")
+def kitti_small(pkg):
+    return pkg.synth.kitti_pair(pair=1, n_points=20_000, n_rings=32, n_az=700)
+
+
+# ------------------------------------------------------------------------------------------------ kNN
+@pytest.mark.parametrize("k", [1, 4, 20])
+def test_knn_bit_exact_room(sicp, oracle, room, k):
+    tgt = sicp.Cloud(room["tgt_xyz"])
+    idx, d2 = sicp.knn(tgt, room["src_xyz"], k)
+    ridx, rd2 = oracle.knn(room["tgt_xyz"], room["src_xyz"], k)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(d2, rd2)
+
+
+@pytest.mark.parametrize("k", [1, 4, 20, 7, 32])
+def test_knn_bit_exact_lidar_with_pose(sicp, oracle, kitti_small, k):
+    p = kitti_small
+    tgt = sicp.Cloud(p["tgt_xyz"])
+    idx, d2 = sicp.knn(tgt, p["src_xyz"], k, pose7=p["T_gt"])
+    q = oracle.transform_points(p["T_gt"], p["src_xyz"])
+    ridx, rd2 = oracle.knn(p["tgt_xyz"], q, k)
+    assert np.array_equal(idx, ridx)
+    assert np.array_equal(d2, rd2)
+
+
+def test_knn_vs_bruteforce_definition(sicp, oracle, kitti_small):
+    p = kitti_small
+    tgt = sicp.Cloud(p["tgt_xyz"])
+    q = p["src_xyz"][:777]
+    idx, d2 = sicp.knn(tgt, q, 4)
+    ridx, rd2 = oracle.knn(p["tgt_xyz"], q, 4, brute=True)
+    assert np.array_equal(idx, ridx) and np.array_equal(d2, rd2)
+
+
+def test_knn_ties_lowest_index(sicp, oracle):
+    # integer lattice => many exactly equal distances; duplicated points => zero-distance ties
+    g = np.stack(np.meshgrid(np.arange(12), np.arange(12), np.arange(6), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(3)
+    tgt_pts = np.concatenate([g, g[rng.integers(0, len(g), 200)]])
+    rng.shuffle(tgt_pts)
+    q = rng.integers(0, 12, size=(500, 3)).astype(np.float32) + 0.5 * rng.integers(0, 2, size=(500, 3)).astype(np.float32)
+    tgt = sicp.Cloud(tgt_pts)
+    for k in (1, 4, 20):
+        idx, d2 = sicp.knn(tgt, q, k)
+        ridx, rd2 = oracle.knn(tgt_pts, q, k, brute=True)
+        assert np.array_equal(d2, rd2)
+        assert np.array_equal(idx, ridx)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 31, 32, 33, 257])
+def test_knn_tiny_and_ragged_targets(sicp, oracle, n):
+    rng = np.random.default_rng(n)
+    tgt_pts = rng.normal(size=(n, 3)).astype(np.float32)
+    q = rng.normal(size=(70, 3)).astype(np.float32)
+    tgt = sicp.Cloud(tgt_pts)
+    for k in (1, 4, 20):
+        idx, d2 = sicp.knn(tgt, q, k)
+        ridx, rd2 = oracle.knn(tgt_pts, q, k, brute=True)
+        assert np.array_equal(idx, ridx)
+        assert np.array_equal(d2[ridx >= 0], rd2[ridx >= 0])
+        assert np.all(np.isinf(d2[ridx < 0]))
+
+
+def test_knn_per_class(sicp, oracle, room):
+    p = room
+    tgt = sicp.Cloud(p["tgt_xyz"], p["tgt_labels"], layout=sicp.CLOUD_PER_CLASS)
+    idx, d2 = sicp.knn(tgt, p["src_xyz"], 1, q_labels=p["src_labels"])
+    for lab in np.unique(p["src_labels"]):
+        qs = np.nonzero(p["src_labels"] == lab)[0]
+        ts = np.nonzero(p["tgt_labels"] == lab)[0]
+        if len(ts) == 0:
+            assert np.all(idx[qs] == -1)
+            continue
+        ridx, rd2 = oracle.knn(p["tgt_xyz"][ts], p["src_xyz"][qs], 1)
+        assert np.array_equal(idx[qs, 0], ts[ridx[:, 0]])
+        assert np.array_equal(d2[qs], rd2)
+
+
+def test_class_order_first_appearance(sicp, oracle, room):
+    c = sicp.Cloud(room["src_xyz"], room["src_labels"], layout=sicp.CLOUD_PER_CLASS)
+    labs, sizes = c.classes()
+    rl, rs, _ = oracle.label_split(room["src_labels"])
+    assert np.array_equal(labs, rl)
+    assert np.array_equal(sizes, np.diff(rs))
+
+
+# ------------------------------------------------------------------------------------------------ covariances / E-step inputs
+def test_covariance_neighbours_normals_label_vectors(sicp, oracle, kitti_small):
+    p = kitti_small
+    c = sicp.Cloud(p["tgt_xyz"], p["tgt_labels"])
+    c.precompute(20, 1e-3, p["cm"])
+    ref = oracle.covariances(p["tgt_xyz"], 20, 1e-3, labels=p["tgt_labels"], N=p["N"], want_nn=True)
+    assert np.array_equal(c.self_neighbours(), ref["nn"])          # neighbour sets, in order: bit-exact
+    nrm = c.normals()
+    assert np.array_equal(nrm, ref["normals"])                      # same Jacobi-SVD operation sequence: bit-exact
+    cov = c.covariances()
+    assert np.max(np.abs(cov - ref["cov"])) <= 1e-12               # I-(1-eps)nn^T vs sum_k v_k u_k u_k^T
+    assert np.array_equal(c.label_distributions(), ref["dist"])    # repeated 1/k additions: bit-exact
+    a_ref = ref["dist"] @ p["cm"]
+    assert np.max(np.abs(c.label_vectors() - a_ref)) <= 1e-14
+
+
+def test_covariance_per_class(sicp, oracle, room):
+    p = room
+    c = sicp.Cloud(p["src_xyz"], p["src_labels"], layout=sicp.CLOUD_PER_CLASS)
+    c.precompute(20, 1e-3)
+    ref = oracle.covariances_per_class(p["src_xyz"], p["src_labels"], 20, 1e-3)
+    assert np.array_equal(c.normals(), ref["normals"])
+    assert np.max(np.abs(c.covariances() - ref["cov"])) <= 1e-12
+
+
+def test_covariance_fewer_points_than_k(sicp, oracle):
+    rng = np.random.default_rng(5)
+    xyz = rng.normal(size=(13, 3)).astype(np.float32)  # divisor stays k=20 (semantic_point_cloud.hpp:60-64)
+    c = sicp.Cloud(xyz)
+    c.precompute(20, 1e-3)
+    ref = oracle.covariances(xyz, 20, 1e-3)
+    assert np.array_equal(c.normals(), ref["normals"])
+
+
+# ------------------------------------------------------------------------------------------------ one pass
+def _algo_setup(sicp, p, algo):
+    if algo == "gicp":
+        return sicp.ALGO_GICP, sicp.Cloud(p["src_xyz"]), sicp.Cloud(p["tgt_xyz"]), sicp.default_options(sicp.ALGO_GICP)
+    if algo == "em":
+        return (sicp.ALGO_EM, sicp.Cloud(p["src_xyz"], p["src_labels"]), sicp.Cloud(p["tgt_xyz"], p["tgt_labels"]),
+                sicp.default_options(sicp.ALGO_EM, cm=p["cm"]))
+    return (sicp.ALGO_SEMANTIC, sicp.Cloud(p["src_xyz"], p["src_labels"], layout=sicp.CLOUD_PER_CLASS),
+            sicp.Cloud(p["tgt_xyz"], p["tgt_labels"], layout=sicp.CLOUD_PER_CLASS), sicp.default_options(sicp.ALGO_SEMANTIC))
+
+
+def _oracle_align(oracle, p, algo):
+    if algo == "gicp":
+        return oracle.align_gicp(p["src_xyz"], p["tgt_xyz"], p["init"])
+    if algo == "em":
+        return oracle.align_em(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["init"])
+    return oracle.align_semantic(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["init"])
+
+
+@pytest.mark.parametrize("algo", ["gicp", "em", "semantic"])
+def test_first_pass_correspondences_and_weights(sicp, oracle, room, algo):
+    a, src, tgt, opts = _algo_setup(sicp, room, algo)
+    idx, w, d2 = sicp.correspondences(a, src, tgt, opts, room["init"])
+    ref = _oracle_align(oracle, room, algo)
+    assert np.array_equal(idx, ref["corr0"])                        # bit-exact index sets (incl. gate / class rules)
+    m = ref["corr0"] >= 0
+    assert np.array_equal(d2[m], ref["d20"][m])
+    assert np.max(np.abs(w - ref["w0"])) <= 1e-12 * max(1.0, np.max(np.abs(ref["w0"])))
+
+
+@pytest.mark.parametrize("algo,loss", [("gicp", 0), ("em", 2)])
+def test_evaluate_cost_gradient_hessian(sicp, oracle, room, algo, loss):
+    p = room
+    a, src, tgt, opts = _algo_setup(sicp, p, algo)
+    idx, w, _ = sicp.correspondences(a, src, tgt, opts, p["init"])
+    scov = oracle.covariances(p["src_xyz"], 20, 1e-3)["cov"]
+    tcov = oracle.covariances(p["tgt_xyz"], 20, 1e-3)["cov"]
+    kc = idx.shape[1]
+    s_idx = np.repeat(np.arange(src.n), kc)[idx.ravel() >= 0]
+    t_idx = idx.ravel()[idx.ravel() >= 0]
+    ww = w.ravel()[idx.ravel() >= 0]
+    rng = np.random.default_rng(1)
+    for trial in range(3):
+        x = oracle.se3_exp(rng.normal(scale=0.02, size=6)) if trial else p["init"]
+        cost, g, H = sicp.evaluate(a, src, tgt, opts, p["init"], x)
+        rc, rg, rH = oracle.eval_problem(p["src_xyz"], scov, p["tgt_xyz"], tcov, s_idx, t_idx, ww, loss, x)
+        assert abs(cost - rc) <= 1e-9 * abs(rc)
+        assert np.max(np.abs(g - rg)) <= 1e-9 * np.max(np.abs(rg))
+        assert np.max(np.abs(H - rH)) <= 1e-9 * np.max(np.abs(rH))
+
+
+# ------------------------------------------------------------------------------------------------ full registrations
+@pytest.mark.parametrize("algo", ["gicp", "em", "semantic"])
+def test_register_pose_parity_room(sicp, oracle, pkg, room, algo):
+    a, src, tgt, opts = _algo_setup(sicp, room, algo)
+    res = sicp.register(a, src, tgt, opts, room["init"])
+    ref = _oracle_align(oracle, room, algo)
+    rot, trans = pkg.synth.pose_error(res["pose"], ref["pose"])
+    assert rot < ROT_TOL and trans < TRANS_TOL, (rot, trans)
+    assert res["outer_iter"] == ref["outer_iter"]
+    n = ref["outer_iter"]
+    for i in range(n):  # every intermediate pose agrees, so the discrete correspondence sequence is the same
+        r, t = pkg.synth.pose_error(res["pass_pose"][i], ref["pass_pose"][i])
+        assert r < ROT_TOL and t < TRANS_TOL, (i, r, t)
+    assert list(res["pass_lm_iters"]) == list(ref["pass_lm_iters"])
+
+
+@pytest.mark.parametrize("algo", ["gicp", "em"])
+def test_register_pose_parity_lidar(sicp, oracle, pkg, kitti_small, algo):
+    p = kitti_small
+    a, src, tgt, opts = _algo_setup(sicp, p, algo)
+    res = sicp.register(a, src, tgt, opts, p["init"])
+    ref = _oracle_align(oracle, p, algo)
+    rot, trans = pkg.synth.pose_error(res["pose"], ref["pose"])
+    assert rot < ROT_TOL and trans < TRANS_TOL, (rot, trans)
+    assert res["outer_iter"] == ref["outer_iter"]
+
+
+def test_register_batch_matches_single(sicp, pkg, room):
+    a, src, tgt, opts = _algo_setup(sicp, room, "em")
+    single = sicp.register(a, src, tgt, opts, room["init"])
+    inits = np.stack([room["init"]] * 5)
+    batch = sicp.register_batch(a, [src] * 5, [tgt] * 5, opts, inits)
+    for b in batch:
+        assert np.array_equal(b["pose"], single["pose"])  # deterministic reductions: bit-identical
+        assert b["outer_iter"] == single["outer_iter"]
+
+
+def test_fused_labels(sicp, oracle, room):
+    p = room
+    a, src, tgt, opts = _algo_setup(sicp, p, "em")
+    got = sicp.fused_labels(src, tgt, opts, p["T_gt"])
+    ref = oracle.fused_labels(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["T_gt"])
+    # arg-max over f64 sums whose summation order differs by <=1e-15: allow a handful of exact-tie flips
+    assert np.mean(got == ref) > 0.9995
+
+
+def test_errors(sicp, room):
+    lab0 = room["src_labels"].copy()
+    lab0[5] = 0
+    c = sicp.Cloud(room["src_xyz"], lab0)
+    with pytest.raises(sicp.SicpError):
+        c.precompute(20, 1e-3, room["cm"])  # label 0 is out of range (em_icp.hpp:301)
+    with pytest.raises(sicp.SicpError):
+        sicp.Cloud(room["src_xyz"], None, layout=sicp.CLOUD_PER_CLASS)
+    g = sicp.Cloud(room["src_xyz"])
+    with pytest.raises(sicp.SicpError):
+        g.normals()  # precompute has not run
