@@ -7,11 +7,11 @@
 // Pruning uses box lower bounds evaluated with the same rounded operation sequence; rounding is monotone, so a
 // box is skipped only if every point in it is strictly farther than the current k-th best.
 //
-// Execution model: one warp owns 32 Morton-consecutive queries (one leaf of the query cloud).  The warp walks the
-// target tree in a fixed left-to-right order with WARP-UNIFORM control flow: a node is entered when any lane still
-// needs it; a surviving leaf is staged into shared memory with one coalesced 512-byte load and every lane scans
-// the 32 candidates from shared memory (broadcast reads).  A seed leaf near the queries is scanned first so that
-// the fixed-order walk starts with a tight bound.
+// Execution model: one warp owns 32 Morton-consecutive queries (one leaf of the query cloud) and walks the target
+// tree as a PACKET with warp-uniform control flow: depth-first, children of a node visited nearest-first (key = the
+// minimum box distance over the 32 lanes), a node entered only if some lane still needs it.  The traversal stack is
+// warp-uniform and lives in shared memory.  A surviving leaf is staged into shared memory with one coalesced
+// 512-byte load and every lane scans the 32 candidates from shared memory (broadcast reads).
 #pragma once
 #include "common.cuh"
 
@@ -20,6 +20,7 @@ namespace sicp {
 constexpr int kMortonBits = 19;                       // per axis; 57-bit code + 7 bits of class rank in the sort key
 constexpr uint64_t kMortonMask = (1ull << 57) - 1;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kStackCap = 8 * kMaxLevels;             // DFS over an 8-ary tree: <= 7 pending siblings per level
 
 __device__ __forceinline__ uint64_t spread3(uint32_t v) {  // 21 -> 63 bits, two zero bits between
   uint64_t x = v & 0x1fffff;
@@ -79,82 +80,88 @@ struct TopK {
   }
 };
 
-// All 32 lanes scan one target leaf.  wbuf: 32 float4 of shared memory private to the warp.
-template <int K>
-__device__ __forceinline__ void scan_leaf(const float4* __restrict__ pts, int slot0, float qx, float qy, float qz, bool valid,
-                                          TopK<K>& L, float4* wbuf) {
-  const int lane = threadIdx.x & 31;
-  const float4 mine = __ldg(&pts[slot0 + lane]);
-  __syncwarp();
-  wbuf[lane] = mine;
-  __syncwarp();
-  if (valid) {
-#pragma unroll 8
-    for (int j = 0; j < kLeaf; j++) {
-      const float4 p = wbuf[j];
-      L.consider(dist2_rn(qx, qy, qz, p), slot0 + j, __float_as_int(p.w), pts);
-    }
-  }
-}
+// Shared memory owned by one warp during a search.
+struct WarpScratch {
+  float4 leaf[kLeaf];        // staged candidates
+  int2 stack[kStackCap];     // x = level << 26 | idx, y = key bits (min box distance over the lanes)
+};
 
-// Fixed-order walk of segment `sg` of the target; leaves [skip_lo, skip_hi] (segment-relative) were already scanned.
+// Packet search of one warp's 32 queries in segment `sg` (warp-uniform).  Exact for every valid lane.
 template <int K>
-__device__ __forceinline__ void tree_walk(const CloudView& tv, const Segment& sg, float qx, float qy, float qz, bool valid, TopK<K>& L,
-                                          int skip_lo, int skip_hi, float4* wbuf) {
-  const int top = sg.nlevels - 1;
-  int level = top, idx = 0;
+__device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& sg, float qx, float qy, float qz, bool valid, TopK<K>& L,
+                                           WarpScratch& ws) {
   if (sg.nleaf == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int top = sg.nlevels - 1;
+  int sp = 0;
+  // virtual root: expand the top level (<= kArity nodes); afterwards pop / expand / scan
+  int level = top + 1, idx = 0;
   for (;;) {
-    const int ni = sg.node_off[level] + idx;
-    const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
-    const float lb = box_lb_rn(qx, qy, qz, lo, hi);
-    const bool need = valid && !(lb > L.worst());
-    bool descend = false;
-    if (__any_sync(kFull, need)) {
-      if (level == 0) {
-        if (idx < skip_lo || idx > skip_hi) scan_leaf<K>(tv.pts, sg.p0 + idx * kLeaf, qx, qy, qz, valid, L, wbuf);
-      } else {
-        descend = true;
+    if (level > 0) {
+      // ---- expand: test the children of (level, idx), push the needed ones nearest-last so the nearest pops first
+      const int cl = level - 1;
+      const int c0 = idx * kArity;
+      const int nc = min(kArity, sg.node_cnt[cl] - c0);
+      unsigned mykey = 0x7f800000u;  // +inf: "not needed"
+      int mychild = 0;
+#pragma unroll
+      for (int j = 0; j < kArity; j++) {
+        if (j < nc) {
+          const int ni = sg.node_off[cl] + c0 + j;
+          const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
+          const float lb = box_lb_rn(qx, qy, qz, lo, hi);
+          const bool need = valid && !(lb > L.worst());
+          const unsigned kmin = __reduce_min_sync(kFull, need ? __float_as_uint(lb) : 0x7f800000u);  // lb >= 0: bit order == value order
+          if (lane == j) { mykey = kmin; mychild = c0 + j; }
+        }
+      }
+      // rank of child `lane` among the 8 (ties by child index); needed children have the smallest ranks
+      int rank = 0;
+#pragma unroll
+      for (int j = 0; j < kArity; j++) {
+        const unsigned kj = __shfl_sync(kFull, mykey, j);
+        rank += (kj < mykey) || (kj == mykey && j < lane);
+      }
+      const unsigned needed = __ballot_sync(kFull, lane < kArity && mykey != 0x7f800000u);
+      const int m = __popc(needed);
+      if (lane < kArity && mykey != 0x7f800000u) ws.stack[sp + (m - 1 - rank)] = make_int2((cl << 26) | mychild, (int)mykey);
+      sp += m;
+      __syncwarp();
+    } else {
+      // ---- leaf: stage 32 candidates through shared memory, every lane scans all of them
+      const int slot0 = sg.p0 + idx * kLeaf;
+      const float4 mine = __ldg(&tv.pts[slot0 + lane]);
+      __syncwarp();
+      ws.leaf[lane] = mine;
+      __syncwarp();
+      if (valid) {
+#pragma unroll(K <= 4 ? 8 : 1)
+        for (int j = 0; j < kLeaf; j++) {
+          const float4 p = ws.leaf[j];
+          L.consider(dist2_rn(qx, qy, qz, p), slot0 + j, __float_as_int(p.w), tv.pts);
+        }
       }
     }
-    if (descend) {
-      level--;
-      idx *= kArity;
-      continue;
+    // ---- pop the next node some lane still needs
+    bool found = false;
+    while (sp > 0) {
+      const int2 e = ws.stack[--sp];
+      // key = min box distance over lanes at push time; bounds only tighten, so this cull is conservative
+      const float wmax = __uint_as_float(__reduce_max_sync(kFull, valid ? __float_as_uint(L.worst()) : 0u));
+      if (__int_as_float(e.y) > wmax) continue;
+      level = e.x >> 26;
+      idx = e.x & ((1 << 26) - 1);
+      if (level == 0) {  // exact per-lane re-test of the leaf box before paying for the scan
+        const int ni = sg.node_off[0] + idx;
+        const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
+        const float lb = box_lb_rn(qx, qy, qz, lo, hi);
+        if (!__any_sync(kFull, valid && !(lb > L.worst()))) continue;
+      }
+      found = true;
+      break;
     }
-    // advance to the next node in pre-order
-    bool done = false;
-    for (;;) {
-      idx++;
-      if (level == top) { done = idx >= sg.node_cnt[top]; break; }
-      if ((idx % kArity) != 0 && idx < sg.node_cnt[level]) break;
-      idx = (idx - 1) / kArity;  // parent; the loop increments to its next sibling
-      level++;
-    }
-    if (done) break;
+    if (!found) break;
   }
-}
-
-// Leaf of segment `sg` whose first Morton code is the last one <= the query's code (any leaf is a valid seed).
-__device__ __forceinline__ int seed_leaf(const CloudView& tv, const Segment& sg, float qx, float qy, float qz) {
-  const uint64_t code = morton57(qx, qy, qz, sg.lo, sg.inv_cell);
-  int lo = 0, hi = sg.nleaf - 1;  // invariant: answer in [lo, hi]
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(&tv.leaf_code[sg.leaf0 + mid]) <= code) lo = mid;
-    else hi = mid - 1;
-  }
-  return lo;
-}
-
-// Complete search of one warp's 32 queries in segment `sg`: seed leaves [seed-1, seed+1], then the pruned walk.
-template <int K>
-__device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& sg, float qx, float qy, float qz, bool valid, int seed,
-                                           TopK<K>& L, float4* wbuf) {
-  if (sg.nleaf == 0) return;
-  const int s0 = max(seed - 1, 0), s1 = min(seed + 1, sg.nleaf - 1);
-  for (int lf = s0; lf <= s1; lf++) scan_leaf<K>(tv.pts, sg.p0 + lf * kLeaf, qx, qy, qz, valid, L, wbuf);
-  tree_walk<K>(tv, sg, qx, qy, qz, valid, L, s0, s1, wbuf);
 }
 
 }  // namespace sicp

@@ -119,7 +119,7 @@ __device__ __forceinline__ void svd3_normal(const double* A, double* normal) {
 template <int K>
 __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, int k, double* __restrict__ nrm, int* __restrict__ selfnn,
                                                                 uint8_t* __restrict__ nbr_label) {
-  __shared__ float4 s_buf[kWarpsPerBlock][kLeaf];
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
   __shared__ Segment s_seg[kWarpsPerBlock];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int leaf = blockIdx.x * kWarpsPerBlock + wib;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, in
   const bool valid = __float_as_int(me.w) >= 0;
   TopK<K> L;
   L.init();
-  knn_search<K>(cv, sg, me.x, me.y, me.z, valid, leaf - sg.leaf0, L, s_buf[wib]);
+  knn_search<K>(cv, sg, me.x, me.y, me.z, valid, L, s_ws[wib]);
   if (!valid) return;
   // moments in kNN order (impl/gicp.hpp:198-222): float*float products rounded to float, double sums, divisor k
   double mean[3] = {0, 0, 0};
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) cross_knn_kernel(CloudView sv, Cloud
                                                              const int* __restrict__ stop, const int* __restrict__ tseg_of_sseg, int kc,
                                                              int* __restrict__ corr, float* __restrict__ d2out) {
   if (stop && *stop) return;
-  __shared__ float4 s_buf[kWarpsPerBlock][kLeaf];
+  __shared__ WarpScratch s_ws[kWarpsPerBlock];
   __shared__ Segment s_seg[kWarpsPerBlock];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int leaf = blockIdx.x * kWarpsPerBlock + wib;
@@ -241,14 +241,7 @@ __global__ void __launch_bounds__(kThreads) cross_knn_kernel(CloudView sv, Cloud
   }
   TopK<K> L;
   L.init();
-  int seed = 0;
-  if (sg.nleaf > 0) {
-    const unsigned vm = __ballot_sync(kFull, valid);
-    const int nvalid = __popc(vm);  // valid lanes are a prefix of the warp
-    const int src_lane = nvalid > 16 ? 16 : 0;
-    seed = seed_leaf(tv, sg, __shfl_sync(kFull, q[0], src_lane), __shfl_sync(kFull, q[1], src_lane), __shfl_sync(kFull, q[2], src_lane));
-  }
-  knn_search<K>(tv, sg, q[0], q[1], q[2], valid, seed, L, s_buf[wib]);
+  knn_search<K>(tv, sg, q[0], q[1], q[2], valid, L, s_ws[wib]);
 #pragma unroll
   for (int c = 0; c < K; c++)
     if (c < kc) {
