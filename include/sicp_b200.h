@@ -78,7 +78,9 @@ typedef struct sicp_result {
   int n_corr_last;      /* residual blocks in the last pass                                                            */
   int flags;            /* bit0: outer cap reached                                                                     */
   int lm_evals_total;   /* residual(+Jacobian) sweeps over the correspondence list                                     */
-  int gpu_launches;     /* kernels launched for this registration                                                      */
+  int gpu_launches;     /* kernels that did work in the outer passes of this registration                              */
+  int d2h_bytes;        /* bytes read back to the host (control block) for this registration                          */
+  int reserved0;
   float stage_ms[SICP_STAGE_COUNT];      /* only when options.profile                                                  */
   int stage_launches[SICP_STAGE_COUNT];
   double pass_pose7[64][7];              /* pose after each outer pass (parity tests)                                  */
@@ -92,6 +94,8 @@ sicp_status sicp_device_count(int* count);
 /* Stream all subsequent calls of this host thread are issued on (a cudaStream_t; NULL = legacy default stream). */
 sicp_status sicp_set_stream(void* cuda_stream);
 void sicp_options_default(int algo, sicp_options* opts);
+/* Kernels launched by this host thread since the library was loaded (cloud builds, precompute, passes). */
+uint64_t sicp_launch_count(void);
 
 /* ---- clouds -------------------------------------------------------------------------------------------------
  * sicp_cloud_create replaces GICP::setSourceCloud/setTargetCloud (gicp.h:42-63), Em...::set*Cloud

@@ -16,6 +16,8 @@ static thread_local std::string g_err;
 static thread_local cudaStream_t g_stream = nullptr;
 void set_error(const std::string& msg) { g_err = msg; }
 cudaStream_t current_stream() { return g_stream; }
+static thread_local uint64_t g_launches = 0;
+void count_launches(int n) { g_launches += (uint64_t)n; }
 
 // ---- bounding box: block reduce + ordered-int atomics -------------------------------------------------------
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -197,6 +199,7 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
                                                      c->d_pts, c->d_label, c->d_slot_of_orig, c->d_leaf_code);
   leaf_box_kernel<<<(c->nleaf * 32 + T - 1) / T, T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_node_lo, c->d_node_hi);
   upper_box_kernel<<<nseg, 256, 0, st>>>(c->d_seg, c->d_node_lo, c->d_node_hi);
+  count_launches(7 + (end_bit + 7) / 8 + 2);  // 7 own kernels + CUB onesweep (histogram, scan, one pass per 8 key bits)
   SICP_CUDA(cudaGetLastError());
   // frame (lo, inv_cell) back into the host copy is not needed: kernels read it from d_seg.
   SICP_CUDA(cudaFreeAsync(d_tmp, st));
@@ -267,6 +270,7 @@ sicp_status sicp_device_count(int* count) {
   *count = c;
   return SICP_OK;
 }
+uint64_t sicp_launch_count(void) { return g_launches; }
 sicp_status sicp_set_stream(void* s) { g_stream = (cudaStream_t)s; return SICP_OK; }
 
 static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, const uint32_t* h_labels, size_t n, int layout,

@@ -33,6 +33,7 @@ void set_error(const std::string& msg);
   } while (0)
 
 cudaStream_t current_stream();
+void count_launches(int n);  // per-thread kernel launch counter (sicp_launch_count)
 
 // ------------------------------------------------------------------ search structure
 constexpr int kLeaf = 32;        // points per leaf == warp size: one warp owns one leaf of queries

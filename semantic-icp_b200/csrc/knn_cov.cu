@@ -306,6 +306,7 @@ sicp_status launch_self_knn_pca(const sicp_cloud* c, int k, double* d_nrm, int* 
     case 20: self_knn_pca_kernel<20><<<grid, kThreads, 0, st>>>(cv, k, d_nrm, d_selfnn, d_nbr_label); break;
     default: self_knn_pca_kernel<32><<<grid, kThreads, 0, st>>>(cv, k, d_nrm, d_selfnn, d_nbr_label); break;
   }
+  count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
 }
@@ -321,6 +322,7 @@ sicp_status launch_cross_knn(const sicp_cloud* src, const sicp_cloud* tgt, const
     case 20: cross_knn_kernel<20><<<grid, kThreads, 0, st>>>(sv, tv, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
     default: cross_knn_kernel<32><<<grid, kThreads, 0, st>>>(sv, tv, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
   }
+  count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
 }
@@ -370,6 +372,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
       SICP_CUDA(cudaMallocAsync(&d_mm, 8, st));
       SICP_CUDA(cudaMemcpyAsync(d_mm, h_mm, 8, cudaMemcpyHostToDevice, st));
       label_range_kernel<<<148, 256, 0, st>>>(c->d_label, c->d_pts, c->nslots, d_mm);
+      count_launches(1);
       SICP_CUDA(cudaMemcpyAsync(h_mm, d_mm, 8, cudaMemcpyDeviceToHost, st));
       SICP_CUDA(cudaStreamSynchronize(st));
       SICP_CUDA(cudaFreeAsync(d_mm, st));
@@ -389,6 +392,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
     if (c->nslots) {
       CloudView cv = c->view();
       label_vector_kernel<<<(c->nslots * 32 + 255) / 256, 256, 0, st>>>(cv, k_cov, N, d_cm, d_nbr, c->d_avec, nullptr);
+      count_launches(1);
       SICP_CUDA(cudaGetLastError());
     }
     SICP_CUDA(cudaFreeAsync(d_nbr, st));

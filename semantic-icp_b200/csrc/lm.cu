@@ -451,6 +451,7 @@ sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMC
   const int n = src->nslots * cfg.kc;
   if (n == 0) return SICP_OK;
   estep_kernel<<<(n + 255) / 256, 256, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.kc, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w, d_ctl);
+  count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
 }
@@ -458,6 +459,7 @@ sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMC
 static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
   void* params[] = {&args};
   SICP_CUDA(cudaLaunchCooperativeKernel((void*)lm_kernel, dim3(grid), dim3(kLmThreads), params, 0, st));
+  count_launches(1);
   return SICP_OK;
 }
 

@@ -109,7 +109,7 @@ struct StageTimer {
 // One registration as a resumable state machine so that several can be interleaved on different streams.
 struct Job {
   int algo; sicp_cloud* src; sicp_cloud* tgt; const sicp_options* opts; LMConfig cfg; Workspace ws; StageTimer tm;
-  sicp_result* out; int enqueued = 0; bool finished = false; int launches = 0;
+  sicp_result* out; int enqueued = 0; bool finished = false; int launches = 0; int d2h = 0;
 
   sicp_status start(const double* init7, cudaStream_t st) {
     std::memset(out, 0, sizeof *out);
@@ -142,6 +142,7 @@ struct Job {
     const int cap = cfg.outer_cap + 2;
     for (int i = 0; i < n && enqueued < cap; i++) SICP_CHECK(enqueue_pass());
     SICP_CUDA(cudaMemcpyAsync(ws.h_ctl, ws.d_ctl, sizeof(RegCtl), cudaMemcpyDeviceToHost, ws.st));
+    d2h += (int)sizeof(RegCtl);
     return SICP_OK;
   }
   // after the stream is synchronised: true when the registration is complete
@@ -154,6 +155,7 @@ struct Job {
     const int np = std::min(c.outer, 64);
     std::memcpy(out->pass_pose7, c.pass_pose, sizeof(double) * 7 * np);
     std::memcpy(out->pass_lm_iters, c.pass_lm_iters, sizeof(int) * np);
+    out->d2h_bytes = d2h;
     out->gpu_launches = c.outer * 3;  // kernels that did work (passes enqueued past convergence return immediately)
     tm.collect(out);
     ws.release();
