@@ -81,6 +81,8 @@ typedef struct sicp_result {
   int gpu_launches;     /* kernels that did work in the outer passes of this registration                              */
   int d2h_bytes;        /* bytes read back to the host (control block) for this registration                          */
   int reserved0;
+  double lm_cycles[6];  /* diagnostics, SM cycles inside the LM kernels: block 0 sweeps, block 0 waits, control sections
+                           (total, partial reduction, state load, LM step) */
   float stage_ms[SICP_STAGE_COUNT];      /* only when options.profile                                                  */
   int stage_launches[SICP_STAGE_COUNT];
   double pass_pose7[64][7];              /* pose after each outer pass (parity tests)                                  */

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <unordered_map>
 #include "common.cuh"
 #include "knn.cuh"
@@ -19,22 +20,56 @@ cudaStream_t current_stream() { return g_stream; }
 static thread_local uint64_t g_launches = 0;
 void count_launches(int n) { g_launches += (uint64_t)n; }
 
+// ---- pinned staging: small host tables go to the device with truly asynchronous copies (a cudaMemcpyAsync from
+// pageable memory synchronises the stream first).  Blocks are recycled once the event recorded after their last
+// use has completed.
+static std::mutex g_pin_mu;
+static std::vector<PinnedBlock> g_pin_pool;
+void* pinned_stage(size_t bytes, cudaStream_t st, PinnedBlock* out) {
+  bytes = std::max<size_t>(bytes, 4096);
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pin_pool.size(); i++)
+      if (g_pin_pool[i].bytes >= bytes && cudaEventQuery(g_pin_pool[i].ev) == cudaSuccess) {
+        *out = g_pin_pool[i];
+        g_pin_pool.erase(g_pin_pool.begin() + i);
+        return out->p;
+      }
+  }
+  out->p = nullptr; out->bytes = bytes;
+  if (cudaMallocHost(&out->p, bytes) != cudaSuccess) return nullptr;
+  cudaEventCreateWithFlags(&out->ev, cudaEventDisableTiming);
+  (void)st;
+  return out->p;
+}
+void pinned_release(PinnedBlock& b, cudaStream_t st) {  // call after the last copy that reads the block was enqueued
+  cudaEventRecord(b.ev, st);
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pin_pool.push_back(b);
+}
+
 // ---- bounding box: block reduce + ordered-int atomics -------------------------------------------------------
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
+// bb[0..5] = ordered-int min/max of xyz; bb[6], bb[7] = min/max label
 __global__ void bbox_init_kernel(int* bb) {
   if (threadIdx.x < 3) bb[threadIdx.x] = f2ord(INFINITY);
   else if (threadIdx.x < 6) bb[threadIdx.x] = f2ord(-INFINITY);
+  else if (threadIdx.x == 6) bb[6] = -1;  // 0xffffffff as unsigned
+  else if (threadIdx.x == 7) bb[7] = 0;
 }
-__global__ void bbox_kernel(const float* __restrict__ xyz, int n, int* bb) {
+__global__ void bbox_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ labels, int n, int* bb) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+  unsigned llo = 0xffffffffu, lhi = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     for (int c = 0; c < 3; c++) {
       float v = xyz[3 * (size_t)i + c];
       lo[c] = fminf(lo[c], v);
       hi[c] = fmaxf(hi[c], v);
     }
+    if (labels) { const unsigned l = labels[i]; llo = min(llo, l); lhi = max(lhi, l); }
+  }
   for (int c = 0; c < 3; c++) {
     for (int o = 16; o; o >>= 1) {
       lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
@@ -45,35 +80,50 @@ __global__ void bbox_kernel(const float* __restrict__ xyz, int n, int* bb) {
       atomicMax(&bb[3 + c], f2ord(hi[c]));
     }
   }
-}
-// writes the quantisation frame into every segment descriptor
-__global__ void frame_kernel(const int* bb, Segment* seg, int nseg) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nseg) return;
-  float lo[3], ext = 0.f;
-  for (int c = 0; c < 3; c++) {
-    lo[c] = ord2f(bb[c]);
-    ext = fmaxf(ext, ord2f(bb[3 + c]) - lo[c]);
+  if (labels) {
+    for (int o = 16; o; o >>= 1) { llo = min(llo, __shfl_xor_sync(0xffffffffu, llo, o)); lhi = max(lhi, __shfl_xor_sync(0xffffffffu, lhi, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin((unsigned*)&bb[6], llo); atomicMax((unsigned*)&bb[7], lhi); }
   }
-  if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
-  for (int c = 0; c < 3; c++) seg[s].lo[c] = lo[c];
-  seg[s].inv_cell = (float)((1u << kMortonBits) - 1) / ext;
 }
-__global__ void key_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rank, int n, const Segment* seg,
-                           uint64_t* keys, uint32_t* vals) {
+// 30-bit Morton code (10 bits per axis) in the cloud's bounding cube; PER_CLASS clouds put the class rank above it
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000ff;
+  v = (v | (v << 8)) & 0x0300f00f;
+  v = (v | (v << 4)) & 0x030c30c3;
+  v = (v | (v << 2)) & 0x09249249;
+  return v;
+}
+template <typename KeyT>
+__global__ void key_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rank, int n, const int* __restrict__ bb, KeyT* keys,
+                           uint32_t* vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-  uint64_t k = morton57(x, y, z, seg[0].lo, seg[0].inv_cell);
-  if (rank) k |= (uint64_t)rank[i] << 57;
+  float lo[3], ext = 0.f;
+  for (int c = 0; c < 3; c++) { lo[c] = ord2f(bb[c]); ext = fmaxf(ext, ord2f(bb[3 + c]) - lo[c]); }
+  if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
+  const float inv_cell = 1023.f / ext;
+  uint32_t m = 0;
+  for (int c = 0; c < 3; c++) {
+    const float f = fminf(fmaxf((xyz[3 * (size_t)i + c] - lo[c]) * inv_cell, 0.f), 1023.f);
+    m |= spread10((uint32_t)f) << c;
+  }
+  KeyT k = m;
+  if (sizeof(KeyT) == 8 && rank) k |= (KeyT)((uint64_t)rank[i] << 32);
   keys[i] = k;
   vals[i] = (uint32_t)i;
 }
+__global__ void seg_of_leaf_kernel(const Segment* __restrict__ seg, int nseg, int nleaf, int* out) {
+  int leaf = blockIdx.x * blockDim.x + threadIdx.x;
+  if (leaf >= nleaf) return;
+  int s = 0;
+  while (s + 1 < nseg && seg[s + 1].leaf0 <= leaf) s++;
+  out[leaf] = s;
+}
 // one thread per slot: gather the sorted point (or a NaN pad) and record the inverse permutation
 __global__ void slot_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ labels, const uint32_t* __restrict__ sorted_idx,
-                            const uint64_t* __restrict__ sorted_keys, const int* __restrict__ seg_of_leaf, const Segment* __restrict__ seg,
-                            const int* __restrict__ seg_start, int nslots, float4* pts, uint32_t* label_out, int* slot_of_orig,
-                            uint64_t* leaf_code) {
+                            const int* __restrict__ seg_of_leaf, const Segment* __restrict__ seg, int nslots, float4* pts,
+                            uint32_t* label_out, int* slot_of_orig) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= nslots) return;
   const int sid = seg_of_leaf[slot / kLeaf];
@@ -81,12 +131,10 @@ __global__ void slot_kernel(const float* __restrict__ xyz, const uint32_t* __res
   float4 p = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(-1));
   uint32_t lab = 0;
   if (r < seg[sid].n) {
-    const int j = seg_start[sid] + r;
-    const uint32_t o = sorted_idx[j];
+    const uint32_t o = sorted_idx[seg[sid].start + r];
     p = make_float4(xyz[3 * (size_t)o], xyz[3 * (size_t)o + 1], xyz[3 * (size_t)o + 2], __int_as_float((int)o));
     if (labels) lab = labels[o];
     slot_of_orig[o] = slot;
-    if ((slot & (kLeaf - 1)) == 0) leaf_code[slot / kLeaf] = sorted_keys[j] & kMortonMask;
   }
   pts[slot] = p;
   label_out[slot] = lab;
@@ -137,18 +185,20 @@ __global__ void pack_xyz_kernel(const float4* __restrict__ pts, int nslots, floa
 }
 
 // -------------------------------------------------------------------------------------------------------------
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Everything here is enqueued on `st`; the function does not wait for the device.
 static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t* d_labels, const uint8_t* d_rank,
                                const std::vector<int>& class_sizes, cudaStream_t st) {
   const int n = (int)c->n;
   const int nseg = (int)class_sizes.size();
   c->nseg = nseg;
   c->h_seg.assign(nseg, Segment());
-  std::vector<int> seg_start(nseg);
   int p0 = 0, leaf0 = 0, node0 = 0, start = 0;
   for (int s = 0; s < nseg; s++) {
     Segment& sg = c->h_seg[s];
     std::memset(&sg, 0, sizeof sg);
-    sg.p0 = p0; sg.n = class_sizes[s]; sg.nleaf = (sg.n + kLeaf - 1) / kLeaf; sg.leaf0 = leaf0;
+    sg.p0 = p0; sg.n = class_sizes[s]; sg.nleaf = (sg.n + kLeaf - 1) / kLeaf; sg.leaf0 = leaf0; sg.start = start;
     sg.label = c->layout == SICP_CLOUD_PER_CLASS ? c->class_labels[s] : 0;
     int cnt = sg.nleaf, l = 0;
     for (;;) {
@@ -157,64 +207,68 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
       cnt = (cnt + kArity - 1) / kArity;
     }
     sg.nlevels = l;
-    seg_start[s] = start;
     start += sg.n; p0 += sg.nleaf * kLeaf; leaf0 += sg.nleaf;
   }
   c->nslots = p0; c->nleaf = leaf0; c->nnodes = node0;
-  std::vector<int> seg_of_leaf(c->nleaf);
-  for (int s = 0; s < nseg; s++) std::fill(seg_of_leaf.begin() + c->h_seg[s].leaf0, seg_of_leaf.begin() + c->h_seg[s].leaf0 + c->h_seg[s].nleaf, s);
 
-  SICP_CUDA(cudaMallocAsync(&c->d_pts, sizeof(float4) * std::max(1, c->nslots), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_label, sizeof(uint32_t) * std::max(1, c->nslots), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_seg_of_leaf, sizeof(int) * std::max(1, c->nleaf), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_seg, sizeof(Segment) * std::max(1, nseg), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_node_lo, sizeof(float4) * std::max(1, c->nnodes), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_node_hi, sizeof(float4) * std::max(1, c->nnodes), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_leaf_code, sizeof(uint64_t) * std::max(1, c->nleaf), st));
-  SICP_CUDA(cudaMallocAsync(&c->d_slot_of_orig, sizeof(int) * std::max(1, n), st));
+  // one persistent slab: pts | label | seg_of_leaf | seg | node_lo | node_hi | slot_of_orig | bb
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += align256(std::max<size_t>(bytes, 16)); return o; };
+  const size_t o_pts = carve(sizeof(float4) * c->nslots), o_lab = carve(sizeof(uint32_t) * c->nslots), o_sol = carve(sizeof(int) * c->nleaf),
+               o_seg = carve(sizeof(Segment) * nseg), o_nlo = carve(sizeof(float4) * c->nnodes), o_nhi = carve(sizeof(float4) * c->nnodes),
+               o_soo = carve(sizeof(int) * n), o_bb = carve(sizeof(int) * 8);
+  SICP_CUDA(cudaMallocAsync(&c->d_slab, off, st));
+  char* base = (char*)c->d_slab;
+  c->d_pts = (float4*)(base + o_pts); c->d_label = (uint32_t*)(base + o_lab); c->d_seg_of_leaf = (int*)(base + o_sol);
+  c->d_seg = (Segment*)(base + o_seg); c->d_node_lo = (float4*)(base + o_nlo); c->d_node_hi = (float4*)(base + o_nhi);
+  c->d_slot_of_orig = (int*)(base + o_soo); c->d_bb = (int*)(base + o_bb);
+
+  PinnedBlock pb;
+  void* stage = pinned_stage(sizeof(Segment) * std::max(1, nseg), st, &pb);
+  if (!stage) { set_error("pinned staging allocation failed"); return SICP_ERR_CUDA; }
+  std::memcpy(stage, c->h_seg.data(), sizeof(Segment) * nseg);
+  SICP_CUDA(cudaMemcpyAsync(c->d_seg, stage, sizeof(Segment) * nseg, cudaMemcpyHostToDevice, st));
+  pinned_release(pb, st);
+  const int T = 256;
+  bbox_init_kernel<<<1, 32, 0, st>>>(c->d_bb);
   if (n == 0) return SICP_OK;
 
-  int* d_seg_start; int* d_bb; uint64_t *d_keys, *d_keys2; uint32_t *d_vals, *d_vals2; void* d_tmp = nullptr; size_t tmp_bytes = 0;
-  SICP_CUDA(cudaMallocAsync(&d_seg_start, sizeof(int) * nseg, st));
-  SICP_CUDA(cudaMallocAsync(&d_bb, sizeof(int) * 6, st));
-  SICP_CUDA(cudaMallocAsync(&d_keys, sizeof(uint64_t) * n, st));
-  SICP_CUDA(cudaMallocAsync(&d_keys2, sizeof(uint64_t) * n, st));
-  SICP_CUDA(cudaMallocAsync(&d_vals, sizeof(uint32_t) * n, st));
-  SICP_CUDA(cudaMallocAsync(&d_vals2, sizeof(uint32_t) * n, st));
-  // small host tables: the source vectors die at return, so these copies are synchronous w.r.t. the host
-  SICP_CUDA(cudaMemcpyAsync(c->d_seg, c->h_seg.data(), sizeof(Segment) * nseg, cudaMemcpyHostToDevice, st));
-  SICP_CUDA(cudaMemcpyAsync(c->d_seg_of_leaf, seg_of_leaf.data(), sizeof(int) * c->nleaf, cudaMemcpyHostToDevice, st));
-  SICP_CUDA(cudaMemcpyAsync(d_seg_start, seg_start.data(), sizeof(int) * nseg, cudaMemcpyHostToDevice, st));
+  // temporaries: keys | keys2 | vals | vals2 | cub
+  const bool wide = d_rank != nullptr;
+  const size_t kb = wide ? 8 : 4;
+  size_t cub_bytes = 0;
+  if (wide) SICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 39, st));
+  else SICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 30, st));
+  size_t toff = 0;
+  auto tcarve = [&](size_t bytes) { size_t o = toff; toff += align256(std::max<size_t>(bytes, 16)); return o; };
+  const size_t t_k1 = tcarve(kb * n), t_k2 = tcarve(kb * n), t_v1 = tcarve(4 * (size_t)n), t_v2 = tcarve(4 * (size_t)n), t_cub = tcarve(cub_bytes);
+  char* tmp;
+  SICP_CUDA(cudaMallocAsync(&tmp, toff, st));
+  uint32_t* vals = (uint32_t*)(tmp + t_v1); uint32_t* vals2 = (uint32_t*)(tmp + t_v2);
 
-  const int T = 256;
-  bbox_init_kernel<<<1, 32, 0, st>>>(d_bb);
-  bbox_kernel<<<std::min((n + T - 1) / T, 296), T, 0, st>>>(d_xyz, n, d_bb);
-  frame_kernel<<<(nseg + 63) / 64, 64, 0, st>>>(d_bb, c->d_seg, nseg);
-  key_kernel<<<(n + T - 1) / T, T, 0, st>>>(d_xyz, d_rank, n, c->d_seg, d_keys, d_vals);
-  const int end_bit = d_rank ? 64 : 57;
-  SICP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, end_bit, st));
-  SICP_CUDA(cudaMallocAsync(&d_tmp, tmp_bytes, st));
-  SICP_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_keys, d_keys2, d_vals, d_vals2, n, 0, end_bit, st));
-  slot_kernel<<<(c->nslots + T - 1) / T, T, 0, st>>>(d_xyz, d_labels, d_vals2, d_keys2, c->d_seg_of_leaf, c->d_seg, d_seg_start, c->nslots,
-                                                     c->d_pts, c->d_label, c->d_slot_of_orig, c->d_leaf_code);
+  bbox_kernel<<<std::min((n + T - 1) / T, 296), T, 0, st>>>(d_xyz, d_labels, n, c->d_bb);
+  if (wide) {
+    key_kernel<uint64_t><<<(n + T - 1) / T, T, 0, st>>>(d_xyz, d_rank, n, c->d_bb, (uint64_t*)(tmp + t_k1), vals);
+    SICP_CUDA(cub::DeviceRadixSort::SortPairs(tmp + t_cub, cub_bytes, (uint64_t*)(tmp + t_k1), (uint64_t*)(tmp + t_k2), vals, vals2, n, 0, 39, st));
+  } else {
+    key_kernel<uint32_t><<<(n + T - 1) / T, T, 0, st>>>(d_xyz, nullptr, n, c->d_bb, (uint32_t*)(tmp + t_k1), vals);
+    SICP_CUDA(cub::DeviceRadixSort::SortPairs(tmp + t_cub, cub_bytes, (uint32_t*)(tmp + t_k1), (uint32_t*)(tmp + t_k2), vals, vals2, n, 0, 30, st));
+  }
+  if (nseg == 1) SICP_CUDA(cudaMemsetAsync(c->d_seg_of_leaf, 0, sizeof(int) * c->nleaf, st));
+  else seg_of_leaf_kernel<<<(c->nleaf + T - 1) / T, T, 0, st>>>(c->d_seg, nseg, c->nleaf, c->d_seg_of_leaf);
+  slot_kernel<<<(c->nslots + T - 1) / T, T, 0, st>>>(d_xyz, d_labels, vals2, c->d_seg_of_leaf, c->d_seg, c->nslots, c->d_pts, c->d_label,
+                                                     c->d_slot_of_orig);
   leaf_box_kernel<<<(c->nleaf * 32 + T - 1) / T, T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_node_lo, c->d_node_hi);
   upper_box_kernel<<<nseg, 256, 0, st>>>(c->d_seg, c->d_node_lo, c->d_node_hi);
-  count_launches(7 + (end_bit + 7) / 8 + 2);  // 7 own kernels + CUB onesweep (histogram, scan, one pass per 8 key bits)
+  count_launches(6 + (nseg > 1) + ((wide ? 39 : 30) + 7) / 8 + 2);  // own kernels + CUB onesweep (histogram, scan, one pass per 8 key bits)
   SICP_CUDA(cudaGetLastError());
-  // frame (lo, inv_cell) back into the host copy is not needed: kernels read it from d_seg.
-  SICP_CUDA(cudaFreeAsync(d_tmp, st));
-  SICP_CUDA(cudaFreeAsync(d_vals2, st)); SICP_CUDA(cudaFreeAsync(d_vals, st));
-  SICP_CUDA(cudaFreeAsync(d_keys2, st)); SICP_CUDA(cudaFreeAsync(d_keys, st));
-  SICP_CUDA(cudaFreeAsync(d_bb, st)); SICP_CUDA(cudaFreeAsync(d_seg_start, st));
-  // seg_of_leaf / h_seg / seg_start are pageable host vectors: wait so they may go out of scope
-  SICP_CUDA(cudaStreamSynchronize(st));
+  SICP_CUDA(cudaFreeAsync(tmp, st));
   return SICP_OK;
 }
 
 // first-appearance class order (pcl_2_semantic.h:24-35) → per-point rank + class sizes
-static sicp_status classify(sicp_cloud* c, const uint32_t* h_labels, size_t n, std::vector<uint8_t>* rank, std::vector<int>* sizes) {
+static sicp_status classify(sicp_cloud* c, const uint32_t* h_labels, size_t n, uint8_t* rank, std::vector<int>* sizes) {
   std::unordered_map<uint32_t, int> idx;
-  rank->resize(n);
   for (size_t i = 0; i < n; i++) {
     auto it = idx.find(h_labels[i]);
     int r;
@@ -225,24 +279,30 @@ static sicp_status classify(sicp_cloud* c, const uint32_t* h_labels, size_t n, s
       c->class_labels.push_back(h_labels[i]);
       sizes->push_back(0);
     } else r = it->second;
-    (*rank)[i] = (uint8_t)r;
+    rank[i] = (uint8_t)r;
     (*sizes)[r]++;
   }
   return SICP_OK;
 }
 
 static sicp_status init_device(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) {
     set_error("no CUDA device available (libsicp_b200 has no CPU fallback)");
     return SICP_ERR_CUDA;
   }
-  SICP_REQUIRE(device >= 0 && device < cnt, "device index out of range");
+  SICP_REQUIRE(device >= 0 && device < cnt && device < 64, "device index out of range");
   SICP_CUDA(cudaSetDevice(device));
-  cudaMemPool_t pool;
-  SICP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t thr = UINT64_MAX;
-  SICP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));  // keep freed blocks cached
+  std::lock_guard<std::mutex> lk(mu);
+  if (!done[device]) {
+    cudaMemPool_t pool;
+    SICP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    SICP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));  // keep freed blocks cached
+    done[device] = true;
+  }
   return SICP_OK;
 }
 
@@ -254,7 +314,7 @@ sicp::CloudView sicp_cloud::view() const {
   CloudView v;
   v.n = (int)n; v.nslots = nslots; v.nseg = nseg;
   v.pts = d_pts; v.label = d_label; v.seg_of_leaf = d_seg_of_leaf; v.seg = d_seg;
-  v.node_lo = d_node_lo; v.node_hi = d_node_hi; v.leaf_code = d_leaf_code;
+  v.node_lo = d_node_lo; v.node_hi = d_node_hi;
   v.nrm = d_nrm; v.avec = d_avec; v.N = pre_N;
   return v;
 }
@@ -273,7 +333,8 @@ sicp_status sicp_device_count(int* count) {
 uint64_t sicp_launch_count(void) { return g_launches; }
 sicp_status sicp_set_stream(void* s) { g_stream = (cudaStream_t)s; return SICP_OK; }
 
-static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, const uint32_t* h_labels, size_t n, int layout,
+// h_labels (nullable) are the caller's labels, label_stride bytes apart, when they live on the host.
+static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, const void* h_labels, size_t label_stride, size_t n, int layout,
                                  int device, sicp_cloud** out) {
   cudaStream_t st = current_stream();
   sicp_cloud* c = new sicp_cloud();
@@ -282,13 +343,24 @@ static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, c
   uint8_t* d_rank = nullptr;
   sicp_status rc = SICP_OK;
   if (layout == SICP_CLOUD_PER_CLASS) {
-    std::vector<uint8_t> rank;
-    rc = classify(c, h_labels, n, &rank, &sizes);
+    PinnedBlock pb;
+    uint8_t* rank = (uint8_t*)pinned_stage(std::max<size_t>(n, 1), st, &pb);
+    std::vector<uint32_t> packed(n);
+    for (size_t i = 0; i < n; i++) std::memcpy(&packed[i], (const char*)h_labels + i * label_stride, 4);
+    if (!rank) { set_error("pinned staging allocation failed"); rc = SICP_ERR_CUDA; }
+    if (rc == SICP_OK) rc = classify(c, packed.data(), n, rank, &sizes);
     if (rc == SICP_OK && n > 0) {
-      if (cudaMallocAsync(&d_rank, n, st) != cudaSuccess || cudaMemcpyAsync(d_rank, rank.data(), n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-          cudaStreamSynchronize(st) != cudaSuccess) { set_error("rank upload failed"); rc = SICP_ERR_CUDA; }
+      if (cudaMallocAsync(&d_rank, n, st) != cudaSuccess || cudaMemcpyAsync(d_rank, rank, n, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_error("rank upload failed"); rc = SICP_ERR_CUDA;
+      }
     }
+    if (rank) pinned_release(pb, st);
   } else sizes.push_back((int)n);
+  if (rc == SICP_OK && h_labels && n) {  // host-side label range (labels must be 1..N for EM, em_icp.hpp:301)
+    uint32_t lo = 0xffffffffu, hi = 0;
+    for (size_t i = 0; i < n; i++) { uint32_t l; std::memcpy(&l, (const char*)h_labels + i * label_stride, 4); lo = std::min(lo, l); hi = std::max(hi, l); }
+    c->min_label = lo; c->max_label = hi; c->label_range_known = true;
+  }
   if (rc == SICP_OK) rc = build_cloud(c, d_xyz, d_labels, d_rank, sizes, st);
   if (d_rank) cudaFreeAsync(d_rank, st);
   if (rc != SICP_OK) { sicp_cloud_destroy(c); return rc; }
@@ -307,18 +379,19 @@ sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* la
   SICP_CHECK(init_device(device));
   cudaStream_t st = current_stream();
   float* d_xyz = nullptr; uint32_t* d_lab = nullptr;
-  std::vector<uint32_t> h_lab;
   SICP_CUDA(cudaMallocAsync(&d_xyz, std::max<size_t>(1, n) * 12, st));
-  if (n) SICP_CUDA(cudaMemcpy2DAsync(d_xyz, 12, xyz, xyz_stride, 12, n, cudaMemcpyHostToDevice, st));
+  if (n) {
+    if (xyz_stride == 12) SICP_CUDA(cudaMemcpyAsync(d_xyz, xyz, 12 * n, cudaMemcpyHostToDevice, st));
+    else SICP_CUDA(cudaMemcpy2DAsync(d_xyz, 12, xyz, xyz_stride, 12, n, cudaMemcpyHostToDevice, st));
+  }
   if (labels) {
     SICP_CUDA(cudaMallocAsync(&d_lab, std::max<size_t>(1, n) * 4, st));
-    if (n) SICP_CUDA(cudaMemcpy2DAsync(d_lab, 4, labels, label_stride, 4, n, cudaMemcpyHostToDevice, st));
-    if (layout == SICP_CLOUD_PER_CLASS) {
-      h_lab.resize(n);
-      for (size_t i = 0; i < n; i++) std::memcpy(&h_lab[i], (const char*)labels + i * label_stride, 4);
+    if (n) {
+      if (label_stride == 4) SICP_CUDA(cudaMemcpyAsync(d_lab, labels, 4 * n, cudaMemcpyHostToDevice, st));
+      else SICP_CUDA(cudaMemcpy2DAsync(d_lab, 4, labels, label_stride, 4, n, cudaMemcpyHostToDevice, st));
     }
   }
-  sicp_status rc = create_common(d_xyz, d_lab, h_lab.data(), n, layout, device, out);
+  sicp_status rc = create_common(d_xyz, d_lab, labels, label_stride, n, layout, device, out);
   cudaFreeAsync(d_xyz, st);
   if (d_lab) cudaFreeAsync(d_lab, st);
   return rc;
@@ -332,20 +405,19 @@ sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_label
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || d_labels, "PER_CLASS layout needs labels");
   SICP_CHECK(init_device(device));
   std::vector<uint32_t> h_lab;
-  if (layout == SICP_CLOUD_PER_CLASS && n) {
+  if (layout == SICP_CLOUD_PER_CLASS && n) {  // the class order is a host-side decision: fetch the labels once
     h_lab.resize(n);
     SICP_CUDA(cudaMemcpyAsync(h_lab.data(), d_labels, n * 4, cudaMemcpyDeviceToHost, current_stream()));
     SICP_CUDA(cudaStreamSynchronize(current_stream()));
   }
-  return create_common(d_xyz, d_labels, h_lab.data(), n, layout, device, out);
+  return create_common(d_xyz, d_labels, h_lab.empty() ? nullptr : h_lab.data(), 4, n, layout, device, out);
 }
 
 void sicp_cloud_destroy(sicp_cloud* c) {
   if (!c) return;
   cudaStream_t st = current_stream();
   cudaSetDevice(c->device);
-  void* bufs[] = {c->d_pts, c->d_label, c->d_seg_of_leaf, c->d_seg, c->d_node_lo, c->d_node_hi, c->d_leaf_code, c->d_slot_of_orig,
-                  c->d_nrm, c->d_avec, c->d_dist, c->d_selfnn};
+  void* bufs[] = {c->d_slab, c->d_nrm, c->d_avec};
   for (void* b : bufs) if (b) cudaFreeAsync(b, st);
   delete c;
 }

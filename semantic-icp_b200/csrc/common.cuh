@@ -35,6 +35,11 @@ void set_error(const std::string& msg);
 cudaStream_t current_stream();
 void count_launches(int n);  // per-thread kernel launch counter (sicp_launch_count)
 
+// pinned staging blocks for small host->device tables (see cloud.cu)
+struct PinnedBlock { void* p; size_t bytes; cudaEvent_t ev; };
+void* pinned_stage(size_t bytes, cudaStream_t st, PinnedBlock* out);
+void pinned_release(PinnedBlock& b, cudaStream_t st);
+
 // ------------------------------------------------------------------ search structure
 constexpr int kLeaf = 32;        // points per leaf == warp size: one warp owns one leaf of queries
 constexpr int kArity = 8;        // children per internal node
@@ -50,10 +55,9 @@ struct Segment {
   int nlevels;                 // levels in the implicit tree; level 0 = leaves
   int node_off[kMaxLevels];    // offset of each level in the node arrays
   int node_cnt[kMaxLevels];
-  int leaf0;                   // index of this segment's first leaf in leaf_code[]
+  int leaf0;                   // index of this segment's first leaf
+  int start;                   // first position of this segment in the key-sorted order
   uint32_t label;              // class label (PER_CLASS) or 0
-  float lo[3];                 // Morton quantisation frame
-  float inv_cell;
 };
 
 // Device view of a cloud, passed to kernels by value.
@@ -67,7 +71,6 @@ struct CloudView {
   const Segment* seg;    // [nseg]
   const float4* node_lo; // node boxes, all segments / levels
   const float4* node_hi;
-  const uint64_t* leaf_code;  // [nleaf_total] Morton code of the first point of each leaf
   const double* nrm;     // [3*nslots] SoA normals nx | ny | nz  (after precompute)
   const double* avec;    // [nslots*N] label vectors a_p = CM^T dist_p (EM)
   int N;
@@ -82,25 +85,25 @@ struct sicp_cloud {
   int nslots = 0, nseg = 0, nleaf = 0, nnodes = 0;
   std::vector<sicp::Segment> h_seg;
   std::vector<uint32_t> class_labels;  // first-appearance order
-  // device buffers
+  // device buffers (the first group is carved out of one slab)
+  void* d_slab = nullptr;
+  int* d_bb = nullptr;            // [8] ordered-int bounding box + label min/max
   float4* d_pts = nullptr;
   uint32_t* d_label = nullptr;
   int* d_seg_of_leaf = nullptr;
   sicp::Segment* d_seg = nullptr;
   float4* d_node_lo = nullptr;
   float4* d_node_hi = nullptr;
-  uint64_t* d_leaf_code = nullptr;
   int* d_slot_of_orig = nullptr;  // [n] inverse permutation
   double* d_nrm = nullptr;
   double* d_avec = nullptr;
-  double* d_dist = nullptr;       // [nslots*N] raw label distributions (kept for parity tests)
-  int* d_selfnn = nullptr;        // [nslots*k] self neighbours (slots)
   // precompute cache key
   bool pre_valid = false;
   int pre_k = 0, pre_N = 0;
   double pre_eps = 0;
   std::vector<double> pre_cm;
   bool has_labels = false;
-  uint32_t max_label = 0;
+  uint32_t min_label = 0, max_label = 0;
+  bool label_range_known = false;
   sicp::CloudView view() const;
 };

@@ -20,6 +20,7 @@ struct RegCtl {
   double last_mse;
   double pass_pose[64][7];
   int pass_lm_iters[64];
+  long long dbg_cycles[8];  // block 0: sweep compute, grid sync + final reduce, LM control, total (accumulated over passes)
 };
 
 struct LMConfig {
@@ -38,13 +39,14 @@ sicp_status make_class_map(const sicp_cloud* src, const sicp_cloud* tgt, int min
 
 // E-step: gate + label-compatibility weight + probability gate (impl/em_icp.hpp:65-89,108; gicp_cost_function.h:75-87)
 sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, double gate_d2, const double* d_pose7,
-                         const int* d_stop, int* d_corr, const float* d_d2, double* d_w, RegCtl* d_ctl, cudaStream_t st);
+                         const int* d_stop, int* d_corr, const float* d_d2, double* d_w, float4* d_gpt, double* d_gnt, RegCtl* d_ctl,
+                         cudaStream_t st);
 // M-step: one inner solve (ceres::Solve at impl/gicp.hpp:149-151) + outer-loop bookkeeping, cooperative kernel
 int lm_grid_blocks(int device);
-sicp_status launch_lm(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, const int* d_corr, const double* d_w, RegCtl* d_ctl,
+sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt, RegCtl* d_ctl,
                       double* d_partials, int grid, cudaStream_t st);
 // Single evaluation (cost, g, H) at a given pose, for parity tests
-sicp_status launch_evaluate(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, const int* d_corr, const double* d_w,
+sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt,
                             const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st);
 // fused labels (impl/em_icp.hpp:202-268)
 sicp_status launch_fused_labels(const sicp_cloud* src, const sicp_cloud* tgt, double eps, double gate_d2, const double* d_pose7, const int* d_corr,

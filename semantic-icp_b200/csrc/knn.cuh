@@ -17,27 +17,15 @@
 
 namespace sicp {
 
-constexpr int kMortonBits = 19;                       // per axis; 57-bit code + 7 bits of class rank in the sort key
-constexpr uint64_t kMortonMask = (1ull << 57) - 1;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kStackCap = 8 * kMaxLevels;             // DFS over an 8-ary tree: <= 7 pending siblings per level
 
-__device__ __forceinline__ uint64_t spread3(uint32_t v) {  // 21 -> 63 bits, two zero bits between
-  uint64_t x = v & 0x1fffff;
-  x = (x | x << 32) & 0x1f00000000ffffull;
-  x = (x | x << 16) & 0x1f0000ff0000ffull;
-  x = (x | x << 8) & 0x100f00f00f00f00full;
-  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
-  x = (x | x << 2) & 0x1249249249249249ull;
-  return x;
-}
-__device__ __forceinline__ uint64_t morton57(float x, float y, float z, const float* lo, float inv_cell) {
-  const float mx = (float)((1u << kMortonBits) - 1);
-  const float fx = fminf(fmaxf((x - lo[0]) * inv_cell, 0.f), mx);
-  const float fy = fminf(fmaxf((y - lo[1]) * inv_cell, 0.f), mx);
-  const float fz = fminf(fmaxf((z - lo[2]) * inv_cell, 0.f), mx);
-  return spread3((uint32_t)fx) | (spread3((uint32_t)fy) << 1) | (spread3((uint32_t)fz) << 2);
-}
+#ifdef SICP_STATS
+static __device__ unsigned long long g_stats[8];  // per warp: 0 node expansions, 1 leaf scans, 3 phase-2 iterations; per lane: 2 insertions
+#define SICP_STAT(i, v) do { if ((threadIdx.x & 31) == 0 || (i) == 2) atomicAdd(&sicp::g_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define SICP_STAT(i, v) do { } while (0)
+#endif
 
 __device__ __forceinline__ float dist2_rn(float qx, float qy, float qz, const float4& p) {
   const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
@@ -50,33 +38,32 @@ __device__ __forceinline__ float box_lb_rn(float qx, float qy, float qz, const f
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// Sorted (ascending) list of the K best (d2, slot) in registers; ties on d2 are broken by the ORIGINAL index, which
-// is fetched from pts[slot].w only when two distances are exactly equal.
+// Sorted (ascending) list of the K best candidates in registers.  A candidate is ONE 64-bit key
+//   key = float_bits(d2) << 32 | original_index
+// d2 >= 0, so unsigned order of the bits is numeric order and the 64-bit unsigned compare IS the lexicographic
+// (d2, original index) order of the exact-kNN contract — no separate tie-break path.
 template <int K>
 struct TopK {
-  float d[K];
-  int s[K];
+  unsigned long long key[K];
+  static constexpr unsigned long long kEmpty = (0x7f800000ull << 32) | 0xffffffffull;  // (+inf, no index)
   __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int i = 0; i < K; i++) { d[i] = INFINITY; s[i] = -1; }
+    for (int i = 0; i < K; i++) key[i] = kEmpty;
   }
-  __device__ __forceinline__ float worst() const { return d[K - 1]; }
-  static __device__ __forceinline__ bool before(float dc, int oc, float de, int se, const float4* __restrict__ pts) {
-    if (dc < de) return true;
-    if (dc == de) return se >= 0 && oc < __float_as_int(pts[se].w);
-    return false;
-  }
-  __device__ __forceinline__ void consider(float dc, int slot, int orig, const float4* __restrict__ pts) {
-    if (!(dc <= d[K - 1])) return;  // also rejects NaN (padding slots)
-    if (!before(dc, orig, d[K - 1], s[K - 1], pts)) return;
+  __device__ __forceinline__ float worst() const { return __uint_as_float((unsigned)(key[K - 1] >> 32)); }
+  __device__ __forceinline__ float dist(int i) const { return __uint_as_float((unsigned)(key[i] >> 32)); }
+  __device__ __forceinline__ int orig(int i) const { return (int)(unsigned)(key[i] & 0xffffffffull); }  // -1 = empty
+  __device__ __forceinline__ void consider(float dc, int oc) {
+    const unsigned long long k = ((unsigned long long)__float_as_uint(dc) << 32) | (unsigned)oc;
+    if (!(k < key[K - 1])) return;  // NaN distances (padding slots) have bit patterns above +inf and never pass
     bool placed = false;
 #pragma unroll
     for (int i = K - 1; i >= 1; --i) {
-      const bool mv = !placed && before(dc, orig, d[i - 1], s[i - 1], pts);
-      if (mv) { d[i] = d[i - 1]; s[i] = s[i - 1]; }
-      else if (!placed) { d[i] = dc; s[i] = slot; placed = true; }
+      const bool mv = !placed && k < key[i - 1];
+      if (mv) key[i] = key[i - 1];
+      else if (!placed) { key[i] = k; placed = true; }
     }
-    if (!placed) { d[0] = dc; s[0] = slot; }
+    if (!placed) key[0] = k;
   }
 };
 
@@ -126,6 +113,7 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       const int m = __popc(needed);
       if (lane < kArity && mykey != 0x7f800000u) ws.stack[sp + (m - 1 - rank)] = make_int2((cl << 26) | mychild, (int)mykey);
       sp += m;
+      SICP_STAT(0, 1);
       __syncwarp();
     } else {
       // ---- leaf: stage 32 candidates through shared memory, every lane scans all of them
@@ -134,12 +122,28 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       __syncwarp();
       ws.leaf[lane] = mine;
       __syncwarp();
+      // phase 1: all 32 distances, remember which candidates pass this lane's current bound (no insertion yet);
+      // phase 2: each lane inserts only its own survivors, so the warp iterates max-over-lanes(popcount) times
+      // instead of once per candidate that ANY lane wants.
+      unsigned pass = 0;
       if (valid) {
-#pragma unroll(K <= 4 ? 8 : 1)
+        const float w0 = L.worst();
+#pragma unroll 8
         for (int j = 0; j < kLeaf; j++) {
-          const float4 p = ws.leaf[j];
-          L.consider(dist2_rn(qx, qy, qz, p), slot0 + j, __float_as_int(p.w), tv.pts);
+          const float dj = dist2_rn(qx, qy, qz, ws.leaf[j]);
+          pass |= (dj <= w0 ? 1u : 0u) << j;
         }
+      }
+      SICP_STAT(1, 1);
+#ifdef SICP_STATS
+      { const unsigned mx = __reduce_max_sync(kFull, (unsigned)__popc(pass)); SICP_STAT(3, mx); }
+#endif
+      while (pass) {
+        const int j = __ffs(pass) - 1;
+        pass &= pass - 1;
+        const float4 p = ws.leaf[j];
+        L.consider(dist2_rn(qx, qy, qz, p), __float_as_int(p.w));
+        SICP_STAT(2, 1);
       }
     }
     // ---- pop the next node some lane still needs

@@ -117,8 +117,8 @@ __device__ __forceinline__ void svd3_normal(const double* A, double* normal) {
 
 // ------------------------------------------------------------------ K1: self kNN + PCA
 template <int K>
-__global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, int k, double* __restrict__ nrm, int* __restrict__ selfnn,
-                                                                uint8_t* __restrict__ nbr_label) {
+__global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, const int* __restrict__ slot_of_orig, int k, double* __restrict__ nrm,
+                                                                int* __restrict__ selfnn, uint8_t* __restrict__ nbr_label) {
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   __shared__ Segment s_seg[kWarpsPerBlock];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -140,14 +140,15 @@ __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, in
   double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    if (j < k && L.s[j] >= 0) {
-      const float4 p = cv.pts[L.s[j]];
+    const int nslot = (j < k && L.orig(j) >= 0) ? slot_of_orig[L.orig(j)] : -1;
+    if (nslot >= 0) {
+      const float4 p = cv.pts[nslot];
       mean[0] += p.x; mean[1] += p.y; mean[2] += p.z;
       c00 += __fmul_rn(p.x, p.x);
       c10 += __fmul_rn(p.y, p.x); c11 += __fmul_rn(p.y, p.y);
       c20 += __fmul_rn(p.z, p.x); c21 += __fmul_rn(p.z, p.y); c22 += __fmul_rn(p.z, p.z);
-      if (selfnn) selfnn[(size_t)slot * k + j] = L.s[j];
-      if (nbr_label) nbr_label[(size_t)slot * kMaxK + j] = (uint8_t)cv.label[L.s[j]];
+      if (selfnn) selfnn[(size_t)slot * k + j] = nslot;
+      if (nbr_label) nbr_label[(size_t)slot * kMaxK + j] = (uint8_t)cv.label[nslot];
     } else if (j < k) {
       if (selfnn) selfnn[(size_t)slot * k + j] = -1;
       if (nbr_label) nbr_label[(size_t)slot * kMaxK + j] = 0;
@@ -195,14 +196,6 @@ __global__ void label_vector_kernel(CloudView cv, int k, int N, const double* __
   if (lane + 32 < N) avec[(size_t)slot * N + lane + 32] = valid ? a1 : 0.0;
 }
 
-__global__ void label_range_kernel(const uint32_t* __restrict__ label, const float4* __restrict__ pts, int nslots, unsigned* mm) {
-  unsigned lo = 0xffffffffu, hi = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nslots; i += gridDim.x * blockDim.x)
-    if (__float_as_int(pts[i].w) >= 0) { lo = min(lo, label[i]); hi = max(hi, label[i]); }
-  for (int o = 16; o; o >>= 1) { lo = min(lo, __shfl_xor_sync(kFull, lo, o)); hi = max(hi, __shfl_xor_sync(kFull, hi, o)); }
-  if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
-}
-
 // ------------------------------------------------------------------ K2: transform + cross kNN
 // p' = float(R p + t) with f64 left-to-right arithmetic (pcl::transformPointCloud<PointT,double>)
 __device__ __forceinline__ void transform_rn(const double* R, const double* t, const float4& p, float* q) {
@@ -213,7 +206,8 @@ __device__ __forceinline__ void transform_rn(const double* R, const double* t, c
 }
 
 template <int K>
-__global__ void __launch_bounds__(kThreads) cross_knn_kernel(CloudView sv, CloudView tv, const double* __restrict__ pose7,
+__global__ void __launch_bounds__(kThreads) cross_knn_kernel(CloudView sv, CloudView tv, const int* __restrict__ tslot_of_orig,
+                                                             const double* __restrict__ pose7,
                                                              const int* __restrict__ stop, const int* __restrict__ tseg_of_sseg, int kc,
                                                              int* __restrict__ corr, float* __restrict__ d2out) {
   if (stop && *stop) return;
@@ -245,8 +239,9 @@ __global__ void __launch_bounds__(kThreads) cross_knn_kernel(CloudView sv, Cloud
 #pragma unroll
   for (int c = 0; c < K; c++)
     if (c < kc) {
-      corr[(size_t)slot * kc + c] = valid ? L.s[c] : -1;
-      d2out[(size_t)slot * kc + c] = valid ? L.d[c] : INFINITY;
+      const int o = valid ? L.orig(c) : -1;
+      corr[(size_t)slot * kc + c] = o >= 0 ? tslot_of_orig[o] : -1;
+      d2out[(size_t)slot * kc + c] = o >= 0 ? L.dist(c) : INFINITY;
     }
 }
 
@@ -301,10 +296,10 @@ sicp_status launch_self_knn_pca(const sicp_cloud* c, int k, double* d_nrm, int* 
   CloudView cv = c->view();
   const int grid = (c->nleaf + kWarpsPerBlock - 1) / kWarpsPerBlock;
   switch (pick_K(k)) {
-    case 1: self_knn_pca_kernel<1><<<grid, kThreads, 0, st>>>(cv, k, d_nrm, d_selfnn, d_nbr_label); break;
-    case 4: self_knn_pca_kernel<4><<<grid, kThreads, 0, st>>>(cv, k, d_nrm, d_selfnn, d_nbr_label); break;
-    case 20: self_knn_pca_kernel<20><<<grid, kThreads, 0, st>>>(cv, k, d_nrm, d_selfnn, d_nbr_label); break;
-    default: self_knn_pca_kernel<32><<<grid, kThreads, 0, st>>>(cv, k, d_nrm, d_selfnn, d_nbr_label); break;
+    case 1: self_knn_pca_kernel<1><<<grid, kThreads, 0, st>>>(cv, c->d_slot_of_orig, k, d_nrm, d_selfnn, d_nbr_label); break;
+    case 4: self_knn_pca_kernel<4><<<grid, kThreads, 0, st>>>(cv, c->d_slot_of_orig, k, d_nrm, d_selfnn, d_nbr_label); break;
+    case 20: self_knn_pca_kernel<20><<<grid, kThreads, 0, st>>>(cv, c->d_slot_of_orig, k, d_nrm, d_selfnn, d_nbr_label); break;
+    default: self_knn_pca_kernel<32><<<grid, kThreads, 0, st>>>(cv, c->d_slot_of_orig, k, d_nrm, d_selfnn, d_nbr_label); break;
   }
   count_launches(1);
   SICP_CUDA(cudaGetLastError());
@@ -317,10 +312,10 @@ sicp_status launch_cross_knn(const sicp_cloud* src, const sicp_cloud* tgt, const
   CloudView sv = src->view(), tv = tgt->view();
   const int grid = (src->nleaf + kWarpsPerBlock - 1) / kWarpsPerBlock;
   switch (pick_K(kc)) {
-    case 1: cross_knn_kernel<1><<<grid, kThreads, 0, st>>>(sv, tv, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
-    case 4: cross_knn_kernel<4><<<grid, kThreads, 0, st>>>(sv, tv, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
-    case 20: cross_knn_kernel<20><<<grid, kThreads, 0, st>>>(sv, tv, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
-    default: cross_knn_kernel<32><<<grid, kThreads, 0, st>>>(sv, tv, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
+    case 1: cross_knn_kernel<1><<<grid, kThreads, 0, st>>>(sv, tv, tgt->d_slot_of_orig, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
+    case 4: cross_knn_kernel<4><<<grid, kThreads, 0, st>>>(sv, tv, tgt->d_slot_of_orig, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
+    case 20: cross_knn_kernel<20><<<grid, kThreads, 0, st>>>(sv, tv, tgt->d_slot_of_orig, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
+    default: cross_knn_kernel<32><<<grid, kThreads, 0, st>>>(sv, tv, tgt->d_slot_of_orig, d_pose7, d_stop, d_tseg_of_sseg, kc, d_corr, d_d2); break;
   }
   count_launches(1);
   SICP_CUDA(cudaGetLastError());
@@ -350,6 +345,17 @@ using namespace sicp;
 
 extern "C" {
 
+// debug counters of the stats build (make stats); zeros otherwise
+sicp_status sicp_debug_stats(unsigned long long* out8, int reset) {
+  for (int i = 0; i < 8; i++) out8[i] = 0;
+#ifdef SICP_STATS
+  SICP_CUDA(cudaDeviceSynchronize());
+  SICP_CUDA(cudaMemcpyFromSymbol(out8, g_stats, sizeof(unsigned long long) * 8));
+  if (reset) { unsigned long long z[8] = {0}; SICP_CUDA(cudaMemcpyToSymbol(g_stats, z, sizeof z)); }
+#endif
+  return SICP_OK;
+}
+
 sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, const double* cm) {
   SICP_REQUIRE(c, "cloud is null");
   SICP_REQUIRE(k_cov >= 1 && k_cov <= kMaxK, "k_cov must be in 1..32");
@@ -367,23 +373,23 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
   uint8_t* d_nbr = nullptr;
   double* d_cm = nullptr;
   if (N > 0) {
-    if (c->max_label == 0 && c->nslots) {  // labels must be 1..N (em_icp.hpp:301 indexes label-1)
-      unsigned* d_mm; unsigned h_mm[2] = {0xffffffffu, 0};
-      SICP_CUDA(cudaMallocAsync(&d_mm, 8, st));
-      SICP_CUDA(cudaMemcpyAsync(d_mm, h_mm, 8, cudaMemcpyHostToDevice, st));
-      label_range_kernel<<<148, 256, 0, st>>>(c->d_label, c->d_pts, c->nslots, d_mm);
-      count_launches(1);
-      SICP_CUDA(cudaMemcpyAsync(h_mm, d_mm, 8, cudaMemcpyDeviceToHost, st));
+    if (!c->label_range_known && c->nslots) {  // device-resident labels: fetch the range computed at build time
+      unsigned h_mm[2];
+      SICP_CUDA(cudaMemcpyAsync(h_mm, c->d_bb + 6, 8, cudaMemcpyDeviceToHost, st));
       SICP_CUDA(cudaStreamSynchronize(st));
-      SICP_CUDA(cudaFreeAsync(d_mm, st));
-      SICP_REQUIRE(h_mm[0] >= 1, "label 0 found: EM-ICP labels must be 1..N");
-      c->max_label = h_mm[1];
+      c->min_label = h_mm[0]; c->max_label = h_mm[1]; c->label_range_known = true;
     }
+    SICP_REQUIRE(c->nslots == 0 || c->min_label >= 1, "label 0 found: EM-ICP labels must be 1..N");  // em_icp.hpp:301 indexes label-1
     SICP_REQUIRE(c->nslots == 0 || (int)c->max_label <= N, "label exceeds n_classes: EM-ICP labels must be 1..N");
     SICP_CUDA(cudaMallocAsync(&d_nbr, (size_t)kMaxK * std::max(1, c->nslots), st));
     SICP_CUDA(cudaMallocAsync(&c->d_avec, sizeof(double) * N * std::max(1, c->nslots), st));
     SICP_CUDA(cudaMallocAsync(&d_cm, sizeof(double) * N * N, st));
-    SICP_CUDA(cudaMemcpyAsync(d_cm, cm, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
+    PinnedBlock pb;
+    void* stage = pinned_stage(sizeof(double) * N * N, st, &pb);
+    if (!stage) { set_error("pinned staging allocation failed"); return SICP_ERR_CUDA; }
+    std::memcpy(stage, cm, sizeof(double) * N * N);
+    SICP_CUDA(cudaMemcpyAsync(d_cm, stage, sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
+    pinned_release(pb, st);
   }
   SICP_CHECK(launch_self_knn_pca(c, k_cov, c->d_nrm, nullptr, d_nbr, st));
   c->pre_k = k_cov; c->pre_eps = eps; c->pre_N = N;
@@ -397,7 +403,6 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
     }
     SICP_CUDA(cudaFreeAsync(d_nbr, st));
     SICP_CUDA(cudaFreeAsync(d_cm, st));
-    SICP_CUDA(cudaStreamSynchronize(st));  // cm is caller memory (may be pageable): do not return before it is consumed
   }
   c->pre_valid = true;
   return SICP_OK;

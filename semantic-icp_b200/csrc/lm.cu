@@ -76,60 +76,27 @@ __device__ __forceinline__ void loss_eval(int algo, double w, double s, double* 
   *rho1 = f1 * g1;
 }
 
-template <bool JAC>
-__device__ __forceinline__ void accumulate_residual(const CloudView& sv, const CloudView& tv, int slot, int ts, double w, const RT& P,
-                                                    double kappa, int algo, double* acc) {
-  double ps[3], ns[3], pt[3], nt[3];
-  load_point(sv, slot, ps, ns);
-  load_point(tv, ts, pt, nt);
-  double m[3], d[3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
-    d[i] = pt[i] - (P.R[3 * i] * ps[0] + P.R[3 * i + 1] * ps[1] + P.R[3 * i + 2] * ps[2] + P.t[i]);
-  }
-  double b[3];
-  apply_Minv(nt, m, d, kappa, b);
-  const double r = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
-  double rho0, rho1;
-  loss_eval(algo, w, r * r, &rho0, &rho1);
-  acc[27] += 0.5 * rho0;
-  if (JAC) {
-    double c[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) c[i] = P.R[i] * b[0] + P.R[3 + i] * b[1] + P.R[6 + i] * b[2];  // R^T b
-    const double nc = kappa * (ns[0] * c[0] + ns[1] * c[1] + ns[2] * c[2]);
-    const double e[3] = {ps[0] + c[0] - nc * ns[0], ps[1] + c[1] - nc * ns[1], ps[2] + c[2] - nc * ns[2]};  // p_s + C_s c
-    const double sr = sqrt(rho1);
-    const double s2 = 2.0 * sr;
-    double J[6];
-    J[0] = -s2 * c[0]; J[1] = -s2 * c[1]; J[2] = -s2 * c[2];
-    J[3] = s2 * (c[1] * e[2] - c[2] * e[1]);
-    J[4] = s2 * (c[2] * e[0] - c[0] * e[2]);
-    J[5] = s2 * (c[0] * e[1] - c[1] * e[0]);
-    const double rc = sr * r;
-    int k = 0;
-#pragma unroll
-    for (int a = 0; a < 6; a++) {
-#pragma unroll
-      for (int bb = 0; bb <= a; bb++) acc[k++] += J[a] * J[bb];
-      acc[21 + a] += J[a] * rc;
-    }
-  }
-}
-
 // ------------------------------------------------------------------ K3: E-step
+// One thread per candidate pair r = slot*kc + c.  Besides the weight it GATHERS the target point and normal of the
+// pair into residual-ordered arrays, so that the many LM sweeps of the pass stream them with coalesced loads instead
+// of repeating the gather.
 __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, double eps, double gate_d2, const double* __restrict__ pose7,
-                             const int* __restrict__ stop, int* __restrict__ corr, const float* __restrict__ d2, double* __restrict__ wout, RegCtl* ctl) {
+                             const int* __restrict__ stop, int* __restrict__ corr, const float* __restrict__ d2, double* __restrict__ wout,
+                             float4* __restrict__ g_pt, double* __restrict__ g_nt, RegCtl* ctl) {
   if (stop && *stop) return;
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = r < sv.nslots * kc;
+  const int ncorr = sv.nslots * kc;
+  const bool live = r < ncorr;
   const int slot = live ? r / kc : 0;
   int ts = live ? corr[r] : -1;
   double w = 0.0;
   if (ts >= 0 && !((double)d2[r] < gate_d2)) { ts = -1; corr[r] = -1; }  // `distSq < 250` (gicp.hpp:70, em_icp.hpp:65)
   if (ts >= 0) {
     w = 1.0;
+    double pt[3], nt[3];
+    load_point(tv, ts, pt, nt);
+    g_pt[r] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], 0.f);
+    g_nt[r] = nt[0]; g_nt[(size_t)ncorr + r] = nt[1]; g_nt[2 * (size_t)ncorr + r] = nt[2];
     if (algo == SICP_ALGO_EM) {
       // label compatibility (em_icp.hpp:84-89) with a_p = CM^T dist_p precomputed per point
       const int N = sv.N;
@@ -141,9 +108,8 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
       RT P;
       quat_to_R(pose7, P.R);
       P.t[0] = pose7[4]; P.t[1] = pose7[5]; P.t[2] = pose7[6];
-      double ps[3], ns[3], pt[3], nt[3], m[3], d[3], b[3];
+      double ps[3], ns[3], m[3], d[3], b[3];
       load_point(sv, slot, ps, ns);
-      load_point(tv, ts, pt, nt);
       for (int i = 0; i < 3; i++) {
         m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
         d[i] = pt[i] - (P.R[3 * i] * ps[0] + P.R[3 * i + 1] * ps[1] + P.R[3 * i + 2] * ps[2] + P.t[i]);
@@ -166,80 +132,177 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
 }
 
 // ------------------------------------------------------------------ K4 + K5: LM
+// Solver state of one inner solve.  It lives in global memory (LMSync::state): after every sweep the LAST block to
+// arrive reduces the block partials, runs the LM control step on this state and publishes the next candidate pose;
+// the other blocks wait on a generation flag.  (One atomic + one flag per LM iteration instead of a grid-wide
+// barrier followed by a redundant reduction in every block.)
 struct LMState {
   double x[7], cand[7];
-  double tot[kAcc];
-  double H[21], g[6], cost;
+  double Hs[36], gs[6];        // Jacobi-scaled Gauss-Newton system at x
+  double g[6], cost;
   double scale[6], diag[6];
   double radius, decrease_factor, x_norm, gmax, model;
-  int reuse_diag, last_successful, invalid, iter, evals, term, done;
+  int reuse_diag, last_successful, invalid, iter, evals, term, done, started;
+};
+struct LMSync {
+  unsigned count;              // blocks that finished the current sweep
+  unsigned flag;               // generation of the last published control step
+  unsigned pad[2];
+  double bcast[8];             // candidate pose [7] + done
+  LMState state;
 };
 enum { TERM_NO_CONV = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_RADIUS = 4, TERM_FAIL = 5 };
 
 __device__ __forceinline__ int tri(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
-__device__ bool chol_solve6(const double* A /*6x6 row-major*/, const double* b, double* x) {
-  double L[36];
-  for (int i = 0; i < 36; i++) L[i] = 0;
-  for (int i = 0; i < 6; i++)
+// (Hs + diag/radius) y = gs by Cholesky, fully unrolled (registers), reciprocal pivots
+__device__ __forceinline__ bool chol_solve6(const double* Hs, const double* dg, double inv_radius, const double* b, double* x) {
+  double L[21], inv[6];
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
     for (int j = 0; j <= i; j++) {
-      double s = A[6 * i + j];
-      for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k];
-      if (i == j) { if (!(s > 0)) return false; L[6 * i + i] = sqrt(s); }
-      else L[6 * i + j] = s / L[6 * j + j];
+      double s = Hs[6 * i + j] + (i == j ? dg[i] * inv_radius : 0.0);
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
+      if (i == j) {
+        ok = ok && (s > 0);
+        inv[i] = rsqrt(s);  // the pivot itself is never needed: only its reciprocal
+      } else {
+        L[i * (i + 1) / 2 + j] = s * inv[j];
+      }
     }
+  }
   double y[6];
-  for (int i = 0; i < 6; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[6 * i + k] * y[k]; y[i] = s / L[6 * i + i]; }
-  for (int i = 5; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < 6; k++) s -= L[6 * k + i] * x[k]; x[i] = s / L[6 * i + i]; }
-  return true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s -= L[i * (i + 1) / 2 + k] * y[k];
+    y[i] = s * inv[i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    double s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s -= L[k * (k + 1) / 2 + i] * x[k];
+    x[i] = s * inv[i];
+  }
+  return ok;
 }
-__device__ double grad_max_norm(const double* x7, const double* g) {
+// T * exp(delta) (local_parameterization_se3.h:22) on the LM critical path: one sincos, reciprocal multiplies and an
+// rsqrt renormalisation instead of the divisions / square roots of the general-purpose se3.cuh routines.
+__device__ __forceinline__ void pose_plus_fast(const double* x7, const double* d, double* out7) {
+  const double* up = d;
+  const double* om = d + 3;
+  const double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+  double imag, real, a, b;  // exp: q = (imag*om, real), V = I + a*Om + b*Om^2
+  if (th2 < 1e-16) {
+    imag = 0.5 - (1.0 / 48.0) * th2;
+    real = 1.0 - (1.0 / 8.0) * th2;
+    a = 0.5 - th2 * (1.0 / 24.0);
+    b = (1.0 / 6.0) - th2 * (1.0 / 120.0);
+  } else {
+    const double inv_th = rsqrt(th2);
+    const double theta = th2 * inv_th;
+    double sh, ch;
+    sincos(0.5 * theta, &sh, &ch);
+    imag = sh * inv_th;
+    real = ch;
+    const double s_th = 2.0 * sh * ch;          // sin(theta)
+    const double omc = 2.0 * sh * sh;           // 1 - cos(theta)
+    const double inv_th2 = inv_th * inv_th;
+    a = omc * inv_th2;
+    b = (theta - s_th) * inv_th2 * inv_th;
+  }
+  const double qe[4] = {imag * om[0], imag * om[1], imag * om[2], real};
+  // t_e = V * upsilon, with Om*u = om x u and Om^2*u = om x (om x u)
+  double c1[3], c2[3], te[3];
+  cross3(om, up, c1);
+  cross3(om, c1, c2);
+#pragma unroll
+  for (int i = 0; i < 3; i++) te[i] = up[i] + a * c1[i] + b * c2[i];
+  // compose: q = q_x * q_e (renormalised), t = t_x + q_x * t_e
+  const double ax = x7[0], ay = x7[1], az = x7[2], aw = x7[3];
+  double q[4];
+  q[3] = aw * qe[3] - ax * qe[0] - ay * qe[1] - az * qe[2];
+  q[0] = aw * qe[0] + ax * qe[3] + ay * qe[2] - az * qe[1];
+  q[1] = aw * qe[1] + ay * qe[3] + az * qe[0] - ax * qe[2];
+  q[2] = aw * qe[2] + az * qe[3] + ax * qe[1] - ay * qe[0];
+  const double inv_n = rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+#pragma unroll
+  for (int i = 0; i < 4; i++) out7[i] = q[i] * inv_n;
+  double rt[3];
+  quat_rot(x7, te, rt);
+#pragma unroll
+  for (int i = 0; i < 3; i++) out7[4 + i] = x7[4 + i] + rt[i];
+}
+
+// Ceres' gradient_max_norm = |x - Plus(x, -g)|_inf, compared with 1e-11.  The exp map is only evaluated when the
+// gradient is small enough for that test to possibly pass (|delta| >= 1e-6 moves some coordinate by >> 1e-11).
+__device__ __forceinline__ double grad_max_norm(const double* x7, const double* g) {
+  double gm = 0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) gm = fmax(gm, fabs(g[j]));
+  if (gm > 1e-6) return INFINITY;
   double ng[6];
   for (int j = 0; j < 6; j++) ng[j] = -g[j];
   double p7[7];
-  pose_to7(pose_plus(pose_from7(x7), ng), p7);
+  pose_plus_fast(x7, ng, p7);
   double m = 0;
   for (int i = 0; i < 7; i++) m = fmax(m, fabs(x7[i] - p7[i]));
   return m;
 }
-__device__ double norm7(const double* a) { double s = 0; for (int i = 0; i < 7; i++) s += a[i] * a[i]; return sqrt(s); }
-
-// after the evaluation at x0 (iteration zero of ceres::TrustRegionMinimizer)
-__device__ void lm_init(LMState& S) {
-  for (int i = 0; i < 21; i++) S.H[i] = S.tot[i];
-  for (int i = 0; i < 6; i++) S.g[i] = S.tot[21 + i];
-  S.cost = S.tot[27];
-  for (int j = 0; j < 6; j++) S.scale[j] = 1.0 / (1.0 + sqrt(S.H[tri(j, j)]));  // Jacobi scaling, computed once
+__device__ __forceinline__ double norm7(const double* a) {
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) s += a[i] * a[i];
+  return sqrt(s);
+}
+// adopt the evaluation in `tot` as the current linearisation point
+__device__ __forceinline__ void lm_adopt(LMState& S, const double* tot, bool first) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) S.g[i] = tot[21 + i];
+  S.cost = tot[27];
+  if (first)
+#pragma unroll
+    for (int j = 0; j < 6; j++) S.scale[j] = 1.0 / (1.0 + sqrt(tot[tri(j, j)]));  // Jacobi scaling, computed once
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    S.gs[a] = S.g[a] * S.scale[a];
+#pragma unroll
+    for (int b = 0; b < 6; b++) S.Hs[6 * a + b] = tot[tri(a, b)] * S.scale[a] * S.scale[b];
+  }
   S.gmax = grad_max_norm(S.x, S.g);
   S.x_norm = norm7(S.x);
-  S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diag = 0; S.last_successful = 1; S.invalid = 0; S.iter = 0; S.term = TERM_NO_CONV;
 }
 // top of the minimizer loop up to the candidate point; sets S.done when the solve terminates
-__device__ void lm_propose(LMState& S, int max_iter) {
+__device__ __forceinline__ void lm_propose(LMState& S, int max_iter) {
   const double gtol = 0.1 * kSophusEps, ptol = 1e-8;
   for (;;) {
     if (S.iter >= max_iter) { S.term = TERM_NO_CONV; S.done = 1; return; }
     if (S.last_successful && S.gmax <= gtol) { S.term = TERM_GRADIENT; S.done = 1; return; }
     if (S.radius <= 1e-32) { S.term = TERM_RADIUS; S.done = 1; return; }
     S.iter++;
-    double Hs[36], gs[6];
-    for (int a = 0; a < 6; a++) {
-      gs[a] = S.g[a] * S.scale[a];
-      for (int b = 0; b < 6; b++) Hs[6 * a + b] = S.H[tri(a, b)] * S.scale[a] * S.scale[b];
-    }
-    if (!S.reuse_diag) for (int j = 0; j < 6; j++) S.diag[j] = fmin(fmax(Hs[7 * j], 1e-6), 1e32);
-    double A[36];
-    for (int i = 0; i < 36; i++) A[i] = Hs[i];
-    for (int j = 0; j < 6; j++) A[7 * j] += S.diag[j] / S.radius;
-    double y[6], step[6];
-    const bool ok = chol_solve6(A, gs, y);
+    if (!S.reuse_diag)
+#pragma unroll
+      for (int j = 0; j < 6; j++) S.diag[j] = fmin(fmax(S.Hs[7 * j], 1e-6), 1e32);
+    double y[6];
+    const bool ok = chol_solve6(S.Hs, S.diag, 1.0 / S.radius, S.gs, y);
     S.reuse_diag = 1;
     double model = 0;
     if (ok) {
       double sg = 0, sHs = 0;
-      for (int a = 0; a < 6; a++) step[a] = -y[a];
-      for (int a = 0; a < 6; a++) { sg += step[a] * gs[a]; for (int b = 0; b < 6; b++) sHs += step[a] * Hs[6 * a + b] * step[b]; }
-      model = -sg - 0.5 * sHs;
+#pragma unroll
+      for (int a = 0; a < 6; a++) {
+        double row = 0;
+#pragma unroll
+        for (int b = 0; b < 6; b++) row += S.Hs[6 * a + b] * y[b];
+        sg += y[a] * S.gs[a];
+        sHs += y[a] * row;
+      }
+      model = sg - 0.5 * sHs;  // step = -y:  -step.gs - 1/2 step.Hs.step
     }
     if (!ok || !(model > 0)) {
       if (++S.invalid >= 5) { S.term = TERM_FAIL; S.done = 1; return; }
@@ -249,143 +312,277 @@ __device__ void lm_propose(LMState& S, int max_iter) {
     S.invalid = 0;
     S.model = model;
     double delta[6];
-    for (int j = 0; j < 6; j++) delta[j] = step[j] * S.scale[j];
-    pose_to7(pose_plus(pose_from7(S.x), delta), S.cand);
+#pragma unroll
+    for (int j = 0; j < 6; j++) delta[j] = -y[j] * S.scale[j];
+    pose_plus_fast(S.x, delta, S.cand);
     double sn = 0;
+#pragma unroll
     for (int i = 0; i < 7; i++) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
     if (sqrt(sn) <= ptol * (S.x_norm + ptol)) { S.term = TERM_PARAMETER; S.done = 1; return; }  // candidate not applied
     return;
   }
 }
-// after the evaluation at the candidate (cost, H, g all available in S.tot)
-__device__ void lm_decide(LMState& S) {
+// One control step after a sweep whose totals are in `tot`: iteration zero, or accept/reject + next proposal.
+__device__ __noinline__ void lm_control(LMState& S, const double* tot, int max_iter) {
+  S.evals++;
+  if (!S.started) {
+    S.started = 1;
+    S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diag = 0; S.last_successful = 1; S.invalid = 0; S.iter = 0; S.term = TERM_NO_CONV;
+    lm_adopt(S, tot, true);
+    lm_propose(S, max_iter);
+    return;
+  }
   const double ftol = 0.1 * kSophusEps;
-  const double cand_cost = S.tot[27];
+  const double cand_cost = tot[27];
   const double cost_change = S.cost - cand_cost;
   if (fabs(cost_change) <= ftol * S.cost) { S.term = TERM_FUNCTION; S.done = 1; return; }  // candidate not applied
   const double rel = cost_change / S.model;
   if (rel > 1e-3) {
+#pragma unroll
     for (int i = 0; i < 7; i++) S.x[i] = S.cand[i];
-    S.x_norm = norm7(S.x);
-    for (int i = 0; i < 21; i++) S.H[i] = S.tot[i];
-    for (int i = 0; i < 6; i++) S.g[i] = S.tot[21 + i];
-    S.cost = cand_cost;
-    S.gmax = grad_max_norm(S.x, S.g);
+    lm_adopt(S, tot, false);
     const double t = 2.0 * rel - 1.0;
-    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
-    S.radius = fmin(1e16, S.radius);
+    S.radius = fmin(1e16, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
     S.decrease_factor = 2.0; S.reuse_diag = 0; S.last_successful = 1;
   } else {
     S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diag = 1; S.last_successful = 0;
   }
+  lm_propose(S, max_iter);
 }
 
 struct LMArgs {
-  CloudView sv, tv;
+  CloudView sv;
   LMConfig cfg;
-  const int* corr;
-  const double* w;
+  const double* w;          // [ncorr] E-step weights (0 = no residual)
+  const float4* g_pt;       // [ncorr] gathered target points
+  const double* g_nt;       // [3][ncorr] gathered target normals
   RegCtl* ctl;
-  double* partials;       // [2][gridDim.x * kAcc]
+  double* partials;         // [gridDim.x * kAcc]
+  LMSync* sync;
   const double* eval_pose;  // != null: evaluate once at this pose, write kAcc totals to eval_out, return
   double* eval_out;
 };
 
-// One full sweep over the correspondence list at pose x7: every block ends with the grid totals in S.tot.
-__device__ void sweep(const LMArgs& a, const double* x7, int buf, LMState& S, double (*s_red)[kAcc], cg::grid_group& grid) {
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Residual sweep at pose x7; leaves this block's 28 partial sums in part[blockIdx.x][:].
+template <int ALGO, int KC>
+__device__ __forceinline__ void sweep(const LMArgs& a, const double* x7, double (*s_red)[kAcc]) {
   RT P;
   quat_to_R(x7, P.R);
   P.t[0] = x7[4]; P.t[1] = x7[5]; P.t[2] = x7[6];
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
-  const int ncorr = a.sv.nslots * a.cfg.kc;
+  const int ncorr = a.sv.nslots * KC;
   const double kappa = 1.0 - a.cfg.eps;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ncorr; r += gridDim.x * blockDim.x) {
-    const int ts = __ldg(&a.corr[r]);
-    if (ts < 0) continue;
     const double w = __ldg(&a.w[r]);
     if (w == 0.0) continue;
-    accumulate_residual<true>(a.sv, a.tv, r / a.cfg.kc, ts, w, P, kappa, a.cfg.algo, acc);
+    const int slot = r / KC;
+    const float4 sp = __ldg(&a.sv.pts[slot]);
+    const float4 tp = __ldg(&a.g_pt[r]);
+    const double ns[3] = {__ldg(&a.sv.nrm[slot]), __ldg(&a.sv.nrm[(size_t)a.sv.nslots + slot]), __ldg(&a.sv.nrm[2 * (size_t)a.sv.nslots + slot])};
+    const double nt[3] = {__ldg(&a.g_nt[r]), __ldg(&a.g_nt[(size_t)ncorr + r]), __ldg(&a.g_nt[2 * (size_t)ncorr + r])};
+    const double ps[3] = {sp.x, sp.y, sp.z};
+    const double pt[3] = {tp.x, tp.y, tp.z};
+    double m[3], d[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
+      d[i] = pt[i] - (P.R[3 * i] * ps[0] + P.R[3 * i + 1] * ps[1] + P.R[3 * i + 2] * ps[2] + P.t[i]);
+    }
+    double b[3];
+    apply_Minv(nt, m, d, kappa, b);
+    const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
+    double rho0, rho1;
+    loss_eval(ALGO, w, res * res, &rho0, &rho1);
+    acc[27] += 0.5 * rho0;
+    double c[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) c[i] = P.R[i] * b[0] + P.R[3 + i] * b[1] + P.R[6 + i] * b[2];  // R^T b
+    const double nc = kappa * (ns[0] * c[0] + ns[1] * c[1] + ns[2] * c[2]);
+    const double e[3] = {ps[0] + c[0] - nc * ns[0], ps[1] + c[1] - nc * ns[1], ps[2] + c[2] - nc * ns[2]};  // p_s + C_s c
+    const double sr = sqrt(rho1);
+    const double s2 = 2.0 * sr;
+    double J[6];
+    J[0] = -s2 * c[0]; J[1] = -s2 * c[1]; J[2] = -s2 * c[2];
+    J[3] = s2 * (c[1] * e[2] - c[2] * e[1]);
+    J[4] = s2 * (c[2] * e[0] - c[0] * e[2]);
+    J[5] = s2 * (c[0] * e[1] - c[1] * e[0]);
+    const double rc = sr * res;
+    int k = 0;
+#pragma unroll
+    for (int p = 0; p < 6; p++) {
+#pragma unroll
+      for (int q = 0; q <= p; q++) acc[k++] += J[p] * J[q];
+      acc[21 + p] += J[p] * rc;
+    }
   }
-  // warp butterfly (fixed order => deterministic), then fixed-order block and grid sums
+  // warp butterfly (fixed order => deterministic), then a fixed-order block sum
 #pragma unroll
   for (int i = 0; i < kAcc; i++)
     for (int o = 16; o; o >>= 1) acc[i] += __shfl_xor_sync(kFullMask, acc[i], o);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // s_red may still be read by the previous round
   if (lane == 0)
 #pragma unroll
     for (int i = 0; i < kAcc; i++) s_red[warp][i] = acc[i];
   __syncthreads();
-  double* part = a.partials + (size_t)buf * gridDim.x * kAcc;
   if (threadIdx.x < kAcc) {
     double s = 0;
+#pragma unroll
     for (int wv = 0; wv < kLmThreads / 32; wv++) s += s_red[wv][threadIdx.x];
-    part[(size_t)blockIdx.x * kAcc + threadIdx.x] = s;
+    a.partials[(size_t)blockIdx.x * kAcc + threadIdx.x] = s;
   }
-  grid.sync();
-  if (threadIdx.x < kAcc * 8) {
-    const int comp = threadIdx.x >> 3, sub = threadIdx.x & 7;
-    double s = 0;
-    for (int b = sub; b < (int)gridDim.x; b += 8) s += __ldcg(&part[(size_t)b * kAcc + comp]);
-    s += __shfl_xor_sync(kFullMask, s, 4);
-    s += __shfl_xor_sync(kFullMask, s, 2);
-    s += __shfl_xor_sync(kFullMask, s, 1);
-    if (sub == 0) S.tot[comp] = s;
+}
+
+// Fixed-order sum of the block partials (done by one block): warp `sub` sums blocks sub, sub+8, ... with independent
+// loads, then the 8 warp sums are added in order.  Result in s_tot[0..27].
+__device__ __forceinline__ void reduce_partials(const double* part, double (*s_red)[kAcc], double* s_tot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double s = 0;
+  if (lane < kAcc) {
+    // up to kMaxPerWarp independent loads in flight per lane (one L2 round trip), then the fixed-order sum
+    constexpr int kMaxPerWarp = 40;  // grids of up to 320 blocks
+    double v[kMaxPerWarp];
+#pragma unroll
+    for (int k = 0; k < kMaxPerWarp; k++) {
+      const int bI = warp + 8 * k;
+      v[k] = bI < (int)gridDim.x ? __ldcg(&part[(size_t)bI * kAcc + lane]) : 0.0;
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPerWarp; k++) s += v[k];
+  }
+  __syncthreads();
+  if (lane < kAcc) s_red[warp][lane] = s;
+  __syncthreads();
+  if (threadIdx.x < kAcc) {
+    double t = 0;
+#pragma unroll
+    for (int wv = 0; wv < kLmThreads / 32; wv++) t += s_red[wv][threadIdx.x];
+    s_tot[threadIdx.x] = t;
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kLmThreads) lm_kernel(LMArgs a) {
-  cg::grid_group grid = cg::this_grid();
+template <int ALGO, int KC>
+__global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
   __shared__ LMState S;
   __shared__ double s_red[kLmThreads / 32][kAcc];
-  if (a.eval_pose) {  // parity-test entry: one evaluation
-    if (threadIdx.x < 7) S.x[threadIdx.x] = a.eval_pose[threadIdx.x];
-    __syncthreads();
-    sweep(a, S.x, 0, S, s_red, grid);
-    if (blockIdx.x == 0 && threadIdx.x < kAcc) a.eval_out[threadIdx.x] = S.tot[threadIdx.x];
-    return;
-  }
-  if (threadIdx.x == 0) S.done = a.ctl->converged;
-  if (threadIdx.x < 7) S.x[threadIdx.x] = a.ctl->pose[threadIdx.x];
+  __shared__ double s_tot[kAcc];
+  __shared__ double s_x[8];  // pose to evaluate [7] + done flag
+  __shared__ int s_last;
+  constexpr int kStateWords = (int)(sizeof(LMState) / sizeof(double));
+  static_assert(sizeof(LMState) % sizeof(double) == 0, "LMState must be a whole number of doubles");
+  LMSync* sy = a.sync;
+  const bool eval_only = a.eval_pose != nullptr;
+  if (threadIdx.x < 7) s_x[threadIdx.x] = eval_only ? a.eval_pose[threadIdx.x] : a.ctl->pose[threadIdx.x];
+  if (threadIdx.x == 7) s_x[7] = eval_only ? 0.0 : (double)a.ctl->converged;
   __syncthreads();
-  if (S.done) return;
-  int buf = 0, evals = 1;
-  sweep(a, S.x, buf, S, s_red, grid);
-  buf ^= 1;
-  if (threadIdx.x == 0) { lm_init(S); lm_propose(S, a.cfg.max_iter); }
-  __syncthreads();
-  while (!S.done) {
-    sweep(a, S.cand, buf, S, s_red, grid);
-    buf ^= 1;
-    evals++;
-    if (threadIdx.x == 0) { lm_decide(S); if (!S.done) lm_propose(S, a.cfg.max_iter); }
+  if (s_x[7] != 0.0) return;  // registration already converged: passes enqueued ahead of the host return at once
+  const unsigned gen0 = ld_acquire(&sy->flag);  // generations continue across launches
+  unsigned gen = gen0;
+  long long t_comp = 0, t_ctl = 0, t_wait = 0, t_red = 0, t_ld = 0, t_lm = 0;
+  const long long t_start = clock64();
+  for (;;) {
+    long long t0 = clock64();
+    sweep<ALGO, KC>(a, s_x, s_red);
+    gen++;
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&sy->count, 1u) == gridDim.x - 1);
+    __syncthreads();
+    t_comp += clock64() - t0;
+    t0 = clock64();
+    if (s_last) {
+      __threadfence();
+      reduce_partials(a.partials, s_red, s_tot);
+      const long long t1 = clock64();
+      t_red += t1 - t0;
+      if (eval_only) {
+        if (threadIdx.x < kAcc) a.eval_out[threadIdx.x] = s_tot[threadIdx.x];
+        if (threadIdx.x == 0) { sy->bcast[7] = 1.0; sy->count = 0; __threadfence(); st_release(&sy->flag, gen); }
+        return;
+      }
+      // bring the solver state in, run the control step, publish
+      double* gs = reinterpret_cast<double*>(&sy->state);
+      double* ss = reinterpret_cast<double*>(&S);
+      const bool first = (gen == gen0 + 1);
+      if (!first) for (int i = threadIdx.x; i < kStateWords; i += blockDim.x) ss[i] = __ldcg(&gs[i]);
+      __syncthreads();
+      const long long t2 = clock64();
+      t_ld += t2 - t1;
+      if (threadIdx.x == 0) {
+        if (first) {
+          for (int i = 0; i < kStateWords; i++) ss[i] = 0.0;
+          for (int i = 0; i < 7; i++) S.x[i] = s_x[i];
+        }
+        lm_control(S, s_tot, a.cfg.max_iter);
+        t_lm += clock64() - t2;
+        if (S.done) {
+          // outer-loop bookkeeping: mse = |log(cur^-1 est)|^2 (impl/gicp.hpp:153), stop rule, pass trace
+          RegCtl* c = a.ctl;
+          double lg[6];
+          pose_log(pose_mul(pose_inv(pose_from7(c->pose)), pose_from7(S.x)), lg);
+          double mse = 0;
+          for (int i = 0; i < 6; i++) mse += lg[i] * lg[i];
+          const int before = c->outer;
+          bool conv;
+          if (ALGO == SICP_ALGO_SEMANTIC) conv = (mse < a.cfg.mse_stop) || (before + 1 > a.cfg.outer_cap);  // count++ first (semantic_icp.hpp:47)
+          else conv = (mse < a.cfg.mse_stop) || (before > a.cfg.outer_cap);
+          if (before < 64) { for (int i = 0; i < 7; i++) c->pass_pose[before][i] = S.x[i]; c->pass_lm_iters[before] = S.iter; }
+          for (int i = 0; i < 7; i++) c->pose[i] = S.x[i];
+          c->outer = before + 1;
+          c->lm_iters_total += S.iter;
+          c->lm_evals_total += S.evals;
+          c->term_last = S.term;
+          c->n_corr_last = c->n_corr_pass;
+          c->n_corr_pass = 0;
+          c->final_cost = S.cost;
+          c->last_mse = mse;
+          if (conv && !(mse < a.cfg.mse_stop)) c->flags |= 1;
+          c->converged = conv ? 1 : 0;
+        }
+        for (int i = 0; i < 7; i++) sy->bcast[i] = S.cand[i];
+        sy->bcast[7] = S.done ? 1.0 : 0.0;
+        sy->count = 0;
+      }
+      __syncthreads();
+      if (!S.done) for (int i = threadIdx.x; i < kStateWords; i += blockDim.x) gs[i] = ss[i];
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) st_release(&sy->flag, gen);
+      t_ctl += clock64() - t0;
+    } else {
+      if (threadIdx.x == 0) while ((int)(ld_acquire(&sy->flag) - gen) < 0) __nanosleep(32);
+      __syncthreads();
+      t_wait += clock64() - t0;
+    }
+    if (eval_only) return;
+    if (threadIdx.x < 8) s_x[threadIdx.x] = __ldcg(&sy->bcast[threadIdx.x]);
+    __syncthreads();
+    if (s_x[7] != 0.0) break;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // outer-loop bookkeeping: mse = |log(cur^-1 est)|^2 (impl/gicp.hpp:153), stop rule, pass trace
-    RegCtl* c = a.ctl;
-    double lg[6];
-    pose_log(pose_mul(pose_inv(pose_from7(c->pose)), pose_from7(S.x)), lg);
-    double mse = 0;
-    for (int i = 0; i < 6; i++) mse += lg[i] * lg[i];
-    const int before = c->outer;
-    bool conv;
-    if (a.cfg.algo == SICP_ALGO_SEMANTIC) conv = (mse < a.cfg.mse_stop) || (before + 1 > a.cfg.outer_cap);  // count++ first (semantic_icp.hpp:47)
-    else conv = (mse < a.cfg.mse_stop) || (before > a.cfg.outer_cap);
-    if (before < 64) { for (int i = 0; i < 7; i++) c->pass_pose[before][i] = S.x[i]; c->pass_lm_iters[before] = S.iter; }
-    for (int i = 0; i < 7; i++) c->pose[i] = S.x[i];
-    c->outer = before + 1;
-    c->lm_iters_total += S.iter;
-    c->lm_evals_total += evals;
-    c->term_last = S.term;
-    c->n_corr_last = c->n_corr_pass;
-    c->n_corr_pass = 0;
-    c->final_cost = S.cost;
-    c->last_mse = mse;
-    if (conv && !(mse < a.cfg.mse_stop)) c->flags |= 1;
-    c->converged = conv ? 1 : 0;
+  if (threadIdx.x == 0) {  // diagnostics: block 0's sweep / wait cycles, everybody's control cycles (only the last arrivals have any)
+    if (blockIdx.x == 0) {
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[0], (unsigned long long)t_comp);
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[1], (unsigned long long)t_wait);
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[3], (unsigned long long)(clock64() - t_start));
+    }
+    if (t_ctl) {
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[2], (unsigned long long)t_ctl);
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[4], (unsigned long long)t_red);
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[5], (unsigned long long)t_ld);
+      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[6], (unsigned long long)t_lm);
+    }
   }
 }
 
@@ -434,12 +631,19 @@ __global__ void fused_labels_kernel(CloudView sv, CloudView tv, double eps, doub
 }
 
 // ------------------------------------------------------------------ host launchers
+static void* lm_entry(int algo) {
+  switch (algo) {
+    case SICP_ALGO_GICP: return (void*)lm_kernel<SICP_ALGO_GICP, 1>;
+    case SICP_ALGO_SEMANTIC: return (void*)lm_kernel<SICP_ALGO_SEMANTIC, 1>;
+    default: return (void*)lm_kernel<SICP_ALGO_EM, 4>;
+  }
+}
 int lm_grid_blocks(int device) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device]) return cached[device];
   int sms = 148, per_sm = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_kernel, kLmThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_kernel<SICP_ALGO_EM, 4>, kLmThreads, 0);
   if (per_sm < 1) per_sm = 1;
   int g = sms * std::min(per_sm, 2);
   if (device >= 0 && device < 64) cached[device] = g;
@@ -447,10 +651,12 @@ int lm_grid_blocks(int device) {
 }
 
 sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, double gate_d2, const double* d_pose7,
-                         const int* d_stop, int* d_corr, const float* d_d2, double* d_w, RegCtl* d_ctl, cudaStream_t st) {
+                         const int* d_stop, int* d_corr, const float* d_d2, double* d_w, float4* d_gpt, double* d_gnt, RegCtl* d_ctl,
+                         cudaStream_t st) {
   const int n = src->nslots * cfg.kc;
   if (n == 0) return SICP_OK;
-  estep_kernel<<<(n + 255) / 256, 256, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.kc, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w, d_ctl);
+  estep_kernel<<<(n + 255) / 256, 256, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.kc, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w,
+                                               d_gpt, d_gnt, d_ctl);
   count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
@@ -458,20 +664,21 @@ sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMC
 
 static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
   void* params[] = {&args};
-  SICP_CUDA(cudaLaunchCooperativeKernel((void*)lm_kernel, dim3(grid), dim3(kLmThreads), params, 0, st));
+  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo), dim3(grid), dim3(kLmThreads), params, 0, st));
   count_launches(1);
   return SICP_OK;
 }
 
-sicp_status launch_lm(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, const int* d_corr, const double* d_w, RegCtl* d_ctl,
+sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt, RegCtl* d_ctl,
                       double* d_partials, int grid, cudaStream_t st) {
-  LMArgs args{src->view(), tgt->view(), cfg, d_corr, d_w, d_ctl, d_partials, nullptr, nullptr};
+  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, d_ctl, d_partials + (size_t)grid * kAcc, reinterpret_cast<LMSync*>(d_partials), nullptr, nullptr};
+  static_assert(sizeof(LMSync) <= sizeof(double) * 148 * kAcc, "LMSync must fit in the first partials slab");
   return launch_lm_args(args, grid, st);
 }
 
-sicp_status launch_evaluate(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, const int* d_corr, const double* d_w,
+sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt,
                             const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st) {
-  LMArgs args{src->view(), tgt->view(), cfg, d_corr, d_w, nullptr, d_partials, d_pose7, d_out28};
+  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, nullptr, d_partials + (size_t)grid * kAcc, reinterpret_cast<LMSync*>(d_partials), d_pose7, d_out28};
   return launch_lm_args(args, grid, st);
 }
 
@@ -479,6 +686,7 @@ sicp_status launch_fused_labels(const sicp_cloud* src, const sicp_cloud* tgt, do
                                 const float* d_d2, uint32_t* d_labels_out, cudaStream_t st) {
   if (src->nslots == 0) return SICP_OK;
   fused_labels_kernel<<<(src->nslots + 127) / 128, 128, 0, st>>>(src->view(), tgt->view(), eps, gate_d2, d_pose7, d_corr, d_d2, d_labels_out);
+  count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
 }

@@ -60,7 +60,7 @@ static void pin_put(RegCtl* p) { std::lock_guard<std::mutex> lk(g_pin_mu); g_pin
 
 // Per-registration device workspace
 struct Workspace {
-  int* d_corr = nullptr; float* d_d2 = nullptr; double* d_w = nullptr; RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
+  int* d_corr = nullptr; float* d_d2 = nullptr; double* d_w = nullptr; float4* d_gpt = nullptr; double* d_gnt = nullptr; RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
   RegCtl* h_ctl = nullptr;  // pinned
   int grid = 0;
   cudaStream_t st = nullptr;
@@ -71,8 +71,11 @@ struct Workspace {
     SICP_CUDA(cudaMallocAsync(&d_corr, sizeof(int) * nc, st));
     SICP_CUDA(cudaMallocAsync(&d_d2, sizeof(float) * nc, st));
     SICP_CUDA(cudaMallocAsync(&d_w, sizeof(double) * nc, st));
+    SICP_CUDA(cudaMallocAsync(&d_gpt, sizeof(float4) * nc, st));
+    SICP_CUDA(cudaMallocAsync(&d_gnt, sizeof(double) * 3 * nc, st));
     SICP_CUDA(cudaMallocAsync(&d_ctl, sizeof(RegCtl), st));
-    SICP_CUDA(cudaMallocAsync(&d_partials, sizeof(double) * 2 * 28 * grid, st));
+    SICP_CUDA(cudaMallocAsync(&d_partials, sizeof(double) * 2 * 28 * grid, st));  // slab 0: LMSync (zeroed), slab 1: block partials
+    SICP_CUDA(cudaMemsetAsync(d_partials, 0, sizeof(double) * 28 * grid, st));
     h_ctl = pin_get();
     if (!h_ctl) { set_error("pinned allocation failed"); return SICP_ERR_CUDA; }
     if (cfg.algo == SICP_ALGO_SEMANTIC) SICP_CHECK(make_class_map(src, tgt, min_class_points, &d_map, st));
@@ -82,6 +85,8 @@ struct Workspace {
     if (d_corr) cudaFreeAsync(d_corr, st);
     if (d_d2) cudaFreeAsync(d_d2, st);
     if (d_w) cudaFreeAsync(d_w, st);
+    if (d_gpt) cudaFreeAsync(d_gpt, st);
+    if (d_gnt) cudaFreeAsync(d_gnt, st);
     if (d_ctl) cudaFreeAsync(d_ctl, st);
     if (d_partials) cudaFreeAsync(d_partials, st);
     if (d_map) cudaFreeAsync(d_map, st);
@@ -128,10 +133,10 @@ struct Job {
     SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, stop, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
     tm.end(st);
     tm.begin(SICP_STAGE_ESTEP, st);
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, stop, ws.d_corr, ws.d_d2, ws.d_w, ws.d_ctl, st));
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, stop, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, ws.d_ctl, st));
     tm.end(st);
     tm.begin(SICP_STAGE_LM, st);
-    SICP_CHECK(launch_lm(src, tgt, cfg, ws.d_corr, ws.d_w, ws.d_ctl, ws.d_partials, ws.grid, st));
+    SICP_CHECK(launch_lm(src, cfg, ws.d_w, ws.d_gpt, ws.d_gnt, ws.d_ctl, ws.d_partials, ws.grid, st));
     tm.end(st);
     launches += 3;
     enqueued++;
@@ -156,6 +161,8 @@ struct Job {
     std::memcpy(out->pass_pose7, c.pass_pose, sizeof(double) * 7 * np);
     std::memcpy(out->pass_lm_iters, c.pass_lm_iters, sizeof(int) * np);
     out->d2h_bytes = d2h;
+    for (int i = 0; i < 3; i++) out->lm_cycles[i] = (double)c.dbg_cycles[i];
+    for (int i = 0; i < 3; i++) out->lm_cycles[3 + i] = (double)c.dbg_cycles[4 + i];
     out->gpu_launches = c.outer * 3;  // kernels that did work (passes enqueued past convergence return immediately)
     tm.collect(out);
     ws.release();
@@ -278,7 +285,7 @@ sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, con
   auto body = [&]() -> sicp_status {
     SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
     SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, nullptr, st));
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, nullptr, st));
     SICP_CUDA(cudaMemcpyAsync(h_corr.data(), ws.d_corr, sizeof(int) * nslot_c, cudaMemcpyDeviceToHost, st));
     SICP_CUDA(cudaMemcpyAsync(h_d2.data(), ws.d_d2, sizeof(float) * nslot_c, cudaMemcpyDeviceToHost, st));
     SICP_CUDA(cudaMemcpyAsync(h_w.data(), ws.d_w, sizeof(double) * nslot_c, cudaMemcpyDeviceToHost, st));
@@ -324,9 +331,9 @@ sicp_status sicp_evaluate(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp
   auto body = [&]() -> sicp_status {
     SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
     SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, nullptr, st));
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, nullptr, st));
     double* d_out = &ws.d_ctl->pass_pose[8][0];
-    SICP_CHECK(launch_evaluate(src, tgt, cfg, ws.d_corr, ws.d_w, &ws.d_ctl->pass_pose[0][0], d_out, ws.d_partials, ws.grid, st));
+    SICP_CHECK(launch_evaluate(src, cfg, ws.d_w, ws.d_gpt, ws.d_gnt, &ws.d_ctl->pass_pose[0][0], d_out, ws.d_partials, ws.grid, st));
     SICP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, st));
     SICP_CUDA(cudaStreamSynchronize(st));
     return SICP_OK;

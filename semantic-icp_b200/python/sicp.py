@@ -32,7 +32,7 @@ class Options(C.Structure):
 
 class Result(C.Structure):
     _fields_ = [("pose7", C.c_double * 7), ("outer_iter", C.c_int), ("lm_iters_total", C.c_int), ("final_cost", C.c_double),
-                ("n_corr_last", C.c_int), ("flags", C.c_int), ("lm_evals_total", C.c_int), ("gpu_launches", C.c_int), ("d2h_bytes", C.c_int), ("reserved0", C.c_int),
+                ("n_corr_last", C.c_int), ("flags", C.c_int), ("lm_evals_total", C.c_int), ("gpu_launches", C.c_int), ("d2h_bytes", C.c_int), ("reserved0", C.c_int), ("lm_cycles", C.c_double * 6),
                 ("stage_ms", C.c_float * 8), ("stage_launches", C.c_int * 8), ("pass_pose7", (C.c_double * 7) * 64),
                 ("pass_lm_iters", C.c_int * 64)]
 
@@ -40,7 +40,7 @@ class Result(C.Structure):
         n = min(self.outer_iter, 64)
         return dict(pose=np.array(self.pose7[:]), outer_iter=self.outer_iter, lm_iters_total=self.lm_iters_total,
                     final_cost=self.final_cost, n_corr_last=self.n_corr_last, flags=self.flags, lm_evals_total=self.lm_evals_total,
-                    gpu_launches=self.gpu_launches, d2h_bytes=self.d2h_bytes, stage_ms=dict(zip(STAGES, self.stage_ms[:])),
+                    gpu_launches=self.gpu_launches, d2h_bytes=self.d2h_bytes, lm_cycles=list(self.lm_cycles[:]), stage_ms=dict(zip(STAGES, self.stage_ms[:])),
                     stage_launches=dict(zip(STAGES, self.stage_launches[:])),
                     pass_pose=np.array([list(self.pass_pose7[i]) for i in range(n)]).reshape(n, 7),
                     pass_lm_iters=np.array(self.pass_lm_iters[:n], dtype=np.int32))

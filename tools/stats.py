@@ -1,0 +1,30 @@
+"""Traversal statistics with the instrumented build (make -C semantic-icp_b200 stats)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import semantic_icp_b200 as pkg
+sicp, synth = pkg.sicp, pkg.synth
+sicp.LIB_PATH = os.path.join(pkg.PKG_ROOT, "lib", "libsicp_b200_stats.so")
+L = sicp.lib()
+def stats(reset=True):
+    out = (C.c_ulonglong * 8)()
+    L.sicp_debug_stats(out, C.c_int(int(reset)))
+    return list(out)
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 120000
+p = synth.kitti_pair(0, n_points=n)
+src, tgt = sicp.Cloud(p["src_xyz"], p["src_labels"]), sicp.Cloud(p["tgt_xyz"], p["tgt_labels"])
+stats()
+nw = (n + 31) // 32
+src.precompute(20, 1e-3, p["cm"])
+s = stats()
+print("self kNN k=20: per warp: node expansions %.1f leaf scans %.1f phase2 iters %.1f ; per query insertions %.1f" % (s[0] / nw, s[1] / nw, s[3] / nw, s[2] / n))
+tgt.precompute(20, 1e-3, p["cm"]); stats()
+for k in (1, 4):
+    for pose, name in ((p["init"], "identity"), (p["T_gt"], "T_gt")):
+        sicp.knn(tgt, p["src_xyz"], k, pose7=pose)
+        s = stats()
+        print("cross kNN k=%d at %s: per warp: node expansions %.1f leaf scans %.1f phase2 iters %.1f ; per query insertions %.1f" % (k, name, s[0] / nw, s[1] / nw, s[3] / nw, s[2] / n))
+opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
+r = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
+cyc = r["lm_cycles"]; ev = r["lm_evals_total"]
+print("LM: evals %d, cycles/eval: sweep %.0f wait %.0f control %.0f (reduce %.0f, state load %.0f, lm step %.0f)" % (ev, cyc[0] / ev, cyc[1] / ev, cyc[2] / ev, cyc[3] / ev, cyc[4] / ev, cyc[5] / ev))
