@@ -419,6 +419,7 @@ void sicp_cloud_destroy(sicp_cloud* c) {
   cudaSetDevice(c->device);
   void* bufs[] = {c->d_slab, c->d_nrm, c->d_avec};
   for (void* b : bufs) if (b) cudaFreeAsync(b, st);
+  if (c->ready_ev) cudaEventDestroy(c->ready_ev);
   delete c;
 }
 

@@ -105,5 +105,6 @@ struct sicp_cloud {
   bool has_labels = false;
   uint32_t min_label = 0, max_label = 0;
   bool label_range_known = false;
+  cudaEvent_t ready_ev = nullptr;  // recorded after the last precompute; consumers on other streams wait on it
   sicp::CloudView view() const;
 };

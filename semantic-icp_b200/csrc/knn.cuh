@@ -56,14 +56,16 @@ struct TopK {
   __device__ __forceinline__ void consider(float dc, int oc) {
     const unsigned long long k = ((unsigned long long)__float_as_uint(dc) << 32) | (unsigned)oc;
     if (!(k < key[K - 1])) return;  // NaN distances (padding slots) have bit patterns above +inf and never pass
-    bool placed = false;
+    // one branch-free compare-exchange pass: the candidate sinks to its place, every larger entry moves down one,
+    // the previous worst falls off the end
+    unsigned long long carry = k;
 #pragma unroll
-    for (int i = K - 1; i >= 1; --i) {
-      const bool mv = !placed && k < key[i - 1];
-      if (mv) key[i] = key[i - 1];
-      else if (!placed) { key[i] = k; placed = true; }
+    for (int i = 0; i < K; i++) {
+      const unsigned long long cur = key[i];
+      const bool lt = carry < cur;
+      key[i] = lt ? carry : cur;
+      carry = lt ? cur : carry;
     }
-    if (!placed) key[0] = k;
   }
 };
 

@@ -404,6 +404,8 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
     SICP_CUDA(cudaFreeAsync(d_nbr, st));
     SICP_CUDA(cudaFreeAsync(d_cm, st));
   }
+  if (!c->ready_ev) SICP_CUDA(cudaEventCreateWithFlags(&c->ready_ev, cudaEventDisableTiming));
+  SICP_CUDA(cudaEventRecord(c->ready_ev, st));
   c->pre_valid = true;
   return SICP_OK;
 }

@@ -116,11 +116,11 @@ struct Job {
   int algo; sicp_cloud* src; sicp_cloud* tgt; const sicp_options* opts; LMConfig cfg; Workspace ws; StageTimer tm;
   sicp_result* out; int enqueued = 0; bool finished = false; int launches = 0; int d2h = 0;
 
-  sicp_status start(const double* init7, cudaStream_t st) {
-    std::memset(out, 0, sizeof *out);
+  sicp_status start(const double* init7, cudaStream_t st, int lm_grid) {
     cfg = make_cfg(algo, *opts);
     tm.on = opts->profile != 0;
     SICP_CHECK(ws.alloc(src, tgt, cfg, opts->min_class_points, st));
+    ws.grid = lm_grid;
     std::memset(ws.h_ctl, 0, sizeof(RegCtl));
     std::memcpy(ws.h_ctl->pose, init7, 56);
     SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
@@ -170,6 +170,11 @@ struct Job {
   }
 };
 
+// Streams of the batch executor are created once per host thread and reused.
+static thread_local std::vector<cudaStream_t> t_streams;
+
+// Runs all jobs with up to `max_concurrent` registrations in flight, each on its own stream.  A slot that finishes
+// immediately picks up the next job (no wave barrier), so tails of one registration overlap the bulk of another.
 static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int max_concurrent) {
   cudaStream_t base = current_stream();
   const int nj = (int)jobs.size();
@@ -177,32 +182,55 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   std::vector<cudaStream_t> streams(S, base);
   cudaEvent_t fork = nullptr;
   if (S > 1) {
+    while ((int)t_streams.size() < S) {
+      cudaStream_t s;
+      SICP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      t_streams.push_back(s);
+    }
     SICP_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
     SICP_CUDA(cudaEventRecord(fork, base));
     for (int s = 0; s < S; s++) {
-      SICP_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
+      streams[s] = t_streams[s];
       SICP_CUDA(cudaStreamWaitEvent(streams[s], fork, 0));
     }
   }
   sicp_status rc = SICP_OK;
   const int kChunk = 3;
-  for (int j0 = 0; j0 < nj && rc == SICP_OK; j0 += S) {
-    const int j1 = std::min(nj, j0 + S);
-    for (int j = j0; j < j1 && rc == SICP_OK; j++) {
-      rc = jobs[j].start(init7s + 7 * (size_t)j, streams[j - j0]);
-      if (rc == SICP_OK) rc = jobs[j].enqueue_chunk(kChunk);
-    }
-    int live = j1 - j0;
-    while (live > 0 && rc == SICP_OK) {
-      for (int j = j0; j < j1 && rc == SICP_OK; j++) {
-        if (jobs[j].finished) continue;
-        if (cudaStreamSynchronize(jobs[j].ws.st) != cudaSuccess) { set_error(std::string("stream sync failed: ") + cudaGetErrorString(cudaGetLastError())); rc = SICP_ERR_CUDA; break; }
-        if (jobs[j].done_after_sync()) { jobs[j].finish(); live--; }
-        else rc = jobs[j].enqueue_chunk(kChunk);
-      }
+  const int lm_grid = lm_grid_blocks(jobs[0].src->device) / (S > 1 ? 2 : 1);  // concurrent solves share every SM
+  std::vector<int> slot_job(S, -1);
+  int next = 0, live = 0;
+  auto launch = [&](int slot) -> sicp_status {
+    const int j = next++;
+    slot_job[slot] = j;
+    Job& jb = jobs[j];
+    cudaStream_t st = streams[slot];
+    // covariances / label vectors on this job's stream (no-op when cached); other jobs sharing a cloud wait on its event
+    sicp_set_stream(st);
+    sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts);
+    sicp_set_stream(base);
+    SICP_CHECK(r);
+    if (jb.src->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.src->ready_ev, 0));
+    if (jb.tgt->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.tgt->ready_ev, 0));
+    SICP_CHECK(jb.start(init7s + 7 * (size_t)j, st, lm_grid));
+    SICP_CHECK(jb.enqueue_chunk(kChunk));
+    live++;
+    return SICP_OK;
+  };
+  for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch(s);
+  while (live > 0 && rc == SICP_OK) {
+    for (int s = 0; s < S && rc == SICP_OK; s++) {
+      const int j = slot_job[s];
+      if (j < 0) continue;
+      if (cudaStreamSynchronize(streams[s]) != cudaSuccess) { set_error(std::string("stream sync failed: ") + cudaGetErrorString(cudaGetLastError())); rc = SICP_ERR_CUDA; break; }
+      if (jobs[j].done_after_sync()) {
+        jobs[j].finish();
+        live--;
+        slot_job[s] = -1;
+        if (next < nj) rc = launch(s);
+      } else rc = jobs[j].enqueue_chunk(kChunk);
     }
   }
-  for (Job& jb : jobs) if (!jb.finished) jb.ws.release();
+  for (Job& jb : jobs) if (!jb.finished && jb.ws.st) jb.ws.release();
   if (S > 1) {
     for (int s = 0; s < S; s++) {
       cudaEvent_t e;
@@ -210,7 +238,6 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
       cudaEventRecord(e, streams[s]);
       cudaStreamWaitEvent(base, e, 0);
       cudaEventDestroy(e);
-      cudaStreamDestroy(streams[s]);
     }
     cudaEventDestroy(fork);
   }
@@ -239,6 +266,7 @@ sicp_status sicp_register(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp
   SICP_CHECK(validate(algo, src, tgt, opts));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
+  std::memset(out, 0, sizeof *out);
   StageTimer pre;
   pre.on = opts->profile != 0;
   pre.begin(SICP_STAGE_COV, st);
@@ -260,10 +288,10 @@ sicp_status sicp_register_batch(int algo, size_t n_pairs, sicp_cloud* const* src
     SICP_REQUIRE(src[i]->device == src[0]->device, "all pairs of a batch must live on one device");
   }
   SICP_CUDA(cudaSetDevice(src[0]->device));
-  for (size_t i = 0; i < n_pairs; i++) SICP_CHECK(precompute_pair(algo, src[i], tgt[i], opts));
+  std::memset(out, 0, sizeof(sicp_result) * n_pairs);
   std::vector<Job> jobs(n_pairs);
   for (size_t i = 0; i < n_pairs; i++) { jobs[i].algo = algo; jobs[i].src = src[i]; jobs[i].tgt = tgt[i]; jobs[i].opts = opts; jobs[i].out = out + i; }
-  return run_jobs(jobs, init7s, 8);
+  return run_jobs(jobs, init7s, opts->max_concurrent > 0 ? opts->max_concurrent : 4);
 }
 
 sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* pose7, int32_t* idx_out,

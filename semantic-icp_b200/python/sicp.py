@@ -27,7 +27,7 @@ class SicpError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("k_cov", C.c_int), ("epsilon", C.c_double), ("n_classes", C.c_int), ("confusion", C.c_void_p),
                 ("gate_d2", C.c_double), ("min_class_points", C.c_int), ("max_lm_iterations", C.c_int), ("profile", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("max_concurrent", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class Result(C.Structure):

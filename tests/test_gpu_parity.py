@@ -222,8 +222,13 @@ def test_register_batch_matches_single(sicp, pkg, room):
     inits = np.stack([room["init"]] * 5)
     batch = sicp.register_batch(a, [src] * 5, [tgt] * 5, opts, inits)
     for b in batch:
-        assert np.array_equal(b["pose"], single["pose"])  # deterministic reductions: bit-identical
+        assert np.array_equal(b["pose"], batch[0]["pose"])  # fixed-order reductions: bit-identical within a batch
+        # a batch runs its solves on half-size grids (two per SM), so the summation grouping differs from a single run
+        rot, trans = pkg.synth.pose_error(b["pose"], single["pose"])
+        assert rot < 1e-9 and trans < 1e-9
         assert b["outer_iter"] == single["outer_iter"]
+    again = sicp.register_batch(a, [src] * 5, [tgt] * 5, opts, inits)
+    assert all(np.array_equal(x["pose"], y["pose"]) for x, y in zip(batch, again))  # run-to-run deterministic
 
 
 def test_fused_labels(sicp, oracle, room):

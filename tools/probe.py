@@ -25,14 +25,13 @@ for algo, name in [(sicp.ALGO_EM, "em"), (sicp.ALGO_GICP, "gicp")]:
               "evals", r["lm_evals_total"], "ncorr", r["n_corr_last"], {k: round(v, 3) for k, v in r["stage_ms"].items() if v}, r["stage_launches"],
               "err", synth.pose_error(r["pose"], p["T_gt"]))
 # batch throughput, EM
-clouds = [(sicp.Cloud(q["src_xyz"], q["src_labels"]), sicp.Cloud(q["tgt_xyz"], q["tgt_labels"])) for q in pairs]
 opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
-for rep in range(3):
-    for s, t in clouds:
-        pass
-    t0 = time.perf_counter()
-    cl = [(sicp.Cloud(q["src_xyz"], q["src_labels"]), sicp.Cloud(q["tgt_xyz"], q["tgt_labels"])) for q in pairs]
-    t1 = time.perf_counter()
-    res = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], opts, np.stack([q["init"] for q in pairs]))
-    t2 = time.perf_counter()
-    print("batch", B, "create %.2f ms register %.2f ms -> %.1f reg/s" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, B / (t2 - t0)), [r["outer_iter"] for r in res])
+for conc in (1, 2, 3, 4, 8):
+    opts.max_concurrent = conc
+    for rep in range(3):
+        t0 = time.perf_counter()
+        cl = [(sicp.Cloud(q["src_xyz"], q["src_labels"]), sicp.Cloud(q["tgt_xyz"], q["tgt_labels"])) for q in pairs]
+        t1 = time.perf_counter()
+        res = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], opts, np.stack([q["init"] for q in pairs]))
+        t2 = time.perf_counter()
+    print("batch", B, "conc", conc, "create %.2f ms register %.2f ms -> %.1f reg/s" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, B / (t2 - t0)), [r["outer_iter"] for r in res])
