@@ -1,0 +1,235 @@
+"""CPU tests (-m "not gpu"): the oracle against the golden fixtures in tests/golden/ and against independent
+references (numpy / scipy).  The fixtures are produced by tests/golden/make_golden.py, which never touches the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def cf():
+    with open(os.path.join(GOLD, "cost_function.json")) as f:
+        return json.load(f)
+
+
+# ------------------------------------------------------------------------------------------------ cost function
+def test_cost_function_survey_known_answer(oracle, cf):
+    """r and the 1x7 Jacobian at identity on the exec/test_gradient.cc:32-50 constants."""
+    ka = cf["survey_known_answer"]
+    r, j7, j6, _ = oracle.cost_eval(cf["ps"], cf["pt"], cf["cs"], cf["ct"], [0, 0, 0, 1, 0, 0, 0])
+    assert abs(r - ka["residual"]) < 1e-9
+    assert np.allclose(j7, ka["jac7"], rtol=1e-10, atol=1e-9)
+
+
+def test_cost_function_vs_numpy_transcription(oracle, cf):
+    for c in cf["cases"]:
+        r, j7, j6, _ = oracle.cost_eval(cf["ps"], cf["pt"], cf["cs"], cf["ct"], c["pose7"])
+        assert abs(r - c["residual"]) <= 1e-11 * abs(c["residual"])
+        assert np.allclose(j7, c["jac7"], rtol=1e-10, atol=1e-8)
+        # the reference's route J7 * Dx_this_mul_exp_x_at_0 equals central differences of r(T exp(delta)) (test_gradient.cc)
+        assert np.allclose(j6, c["jac6_numeric"], rtol=2e-6, atol=1e-4)
+
+
+def test_local_jacobian_closed_form(oracle, cf):
+    """J_ups = R^T(dr/dt), J_om = 2 c x (p_s + C_s c) with c = R^T M d — the form the CUDA M-step uses."""
+    ps, pt, cs, ct = (np.array(cf[k], dtype=np.float64) for k in ("ps", "pt", "cs", "ct"))
+    for c in cf["cases"]:
+        p = np.array(c["pose7"])
+        R = oracle.se3_matrix(p)[:3, :3]
+        M = np.linalg.inv(ct + R @ cs @ R.T)
+        d = pt - (R @ ps + p[4:])
+        cc = R.T @ (M @ d)
+        closed = np.concatenate([-2 * cc, 2 * np.cross(cc, ps + cs @ cc)])
+        _, _, j6, _ = oracle.cost_eval(ps, pt, cs, ct, p)
+        assert np.allclose(j6, closed, rtol=1e-11, atol=1e-9)
+
+
+def test_probability_is_a_bool_gate(oracle, cf):
+    """gicp_cost_function.h:75-87 returns the density converted to bool: only exact underflow gives 0."""
+    eye = np.eye(3)
+    p_near = oracle.cost_eval([0, 0, 0], [0.1, 0, 0], eye, eye, [0, 0, 0, 1, 0, 0, 0])[3]
+    p_far = oracle.cost_eval([0, 0, 0], [80, 0, 0], eye, eye, [0, 0, 0, 1, 0, 0, 0])[3]
+    assert p_near > 0 and p_far == 0.0  # mahalanobis^2 = 3200 > ~1490 underflows
+
+
+# ------------------------------------------------------------------------------------------------ losses
+@pytest.mark.parametrize("s", [0.0, 1e-8, 0.3, 4.0, 250.0])
+def test_loss_compositions(oracle, s):
+    eps = np.finfo(np.float64).eps
+    g = np.sqrt(s + eps)
+    rho = oracle.loss(0, 1.0, s)  # Composed(Cauchy(3), SQLoss)
+    assert np.isclose(rho[0], 9 * np.log1p(g / 9), rtol=1e-13)
+    assert np.isclose(rho[1], 1 / (1 + g / 9) / (2 * g), rtol=1e-13)
+    assert rho[2] <= 0
+    rw = oracle.loss(2, 0.37, s)  # Scaled by w
+    assert np.allclose(rw, 0.37 * rho, rtol=1e-14)
+    rs = oracle.loss(1, 1.0, s)   # Cauchy(1.5)
+    assert np.isclose(rs[0], 2.25 * np.log1p(s / 2.25), rtol=1e-13) and np.isclose(rs[1], 1 / (1 + s / 2.25), rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------------ SE(3)
+def test_se3_against_scipy(oracle):
+    with open(os.path.join(GOLD, "se3.json")) as f:
+        items = json.load(f)
+
+    def same_pose(a, b):
+        a, b = np.array(a), np.array(b)
+        if np.dot(a[:4], b[:4]) < 0:
+            b = np.concatenate([-b[:4], b[4:]])
+        return np.allclose(a, b, atol=1e-12)
+
+    for it in items:
+        T = oracle.se3_exp(it["delta"])
+        assert same_pose(T, it["pose7"])
+        assert np.allclose(oracle.se3_log(T), it["delta"], atol=1e-11)
+        Tb = oracle.se3_exp(it["delta_b"])
+        assert same_pose(oracle.se3_mul(T, Tb), it["pose7_ab"])
+        assert same_pose(oracle.se3_plus(T, it["delta_b"]), it["pose7_ab"])  # Plus = T * exp(delta)
+        assert same_pose(oracle.se3_inv(T), it["pose7_inv"])
+
+
+def test_se3_dx_this_mul_exp_is_the_derivative(oracle):
+    rng = np.random.default_rng(2)
+    T = oracle.se3_exp(rng.normal(size=6))
+    J = oracle.se3_dx(T)
+    h = 1e-7
+    for a in range(6):
+        e = np.zeros(6)
+        e[a] = h
+        num = (oracle.se3_plus(T, e) - oracle.se3_plus(T, -e)) / (2 * h)
+        assert np.allclose(J[:, a], num, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------ kNN
+def test_knn_golden(oracle):
+    z = np.load(os.path.join(GOLD, "knn.npz"))
+    assert bool(z["flann_checked"])
+    for brute in (True, False):
+        idx, d2 = oracle.knn(z["tgt"], z["qry"], 20, brute=brute)
+        assert np.array_equal(idx, z["idx"]) and np.array_equal(d2, z["d2"])
+    idx4, _ = oracle.knn(z["tgt"], z["qry"], 4)
+    assert np.array_equal(idx4, z["idx"][:, :4])
+
+
+def test_knn_tree_equals_bruteforce_with_ties(oracle):
+    g = np.stack(np.meshgrid(np.arange(9), np.arange(9), np.arange(5), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 9, size=(200, 3)).astype(np.float32) + 0.5
+    for k in (1, 4, 20):
+        a = oracle.knn(g, q, k, brute=True)
+        b = oracle.knn(g, q, k, brute=False)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_transform_is_f64_then_f32(oracle):
+    rng = np.random.default_rng(1)
+    xyz = (rng.normal(size=(1000, 3)) * 30).astype(np.float32)
+    T = oracle.se3_exp(rng.normal(size=6) * 0.3)
+    M = oracle.se3_matrix(T)
+    x = xyz.astype(np.float64)
+    ref = np.stack([((M[r, 0] * x[:, 0] + M[r, 1] * x[:, 1]) + M[r, 2] * x[:, 2]) + M[r, 3] for r in range(3)], axis=1).astype(np.float32)
+    assert np.array_equal(oracle.transform_points(T, xyz), ref)
+
+
+# ------------------------------------------------------------------------------------------------ covariances
+def test_jacobi_svd_picks_smallest_magnitude(oracle):
+    rng = np.random.default_rng(4)
+    for _ in range(200):
+        Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        lam = rng.normal(size=3) * np.array([1.0, 0.1, 1e-3])  # includes negative eigenvalues
+        A = (Q * lam) @ Q.T
+        A = 0.5 * (A + A.T)
+        U, sv = oracle.jacobi_svd(A)
+        assert np.allclose(sv, np.sort(np.abs(lam))[::-1], rtol=1e-9, atol=1e-15)
+        assert np.allclose(U.T @ U, np.eye(3), atol=1e-13)
+        u3 = Q[:, np.argmin(np.abs(lam))]
+        assert min(np.linalg.norm(U[:, 2] - u3), np.linalg.norm(U[:, 2] + u3)) < 1e-6 / max(1e-6, np.min(np.diff(np.sort(np.abs(lam)))))
+
+
+def test_covariance_semantics(oracle):
+    rng = np.random.default_rng(7)
+    xyz = rng.normal(size=(400, 3)).astype(np.float32) * np.array([5, 5, 0.01], dtype=np.float32) + np.float32(40.0)
+    labels = rng.integers(1, 6, size=400).astype(np.uint32)
+    out = oracle.covariances(xyz, 20, 1e-3, labels=labels, N=5, want_nn=True)
+    nn, _ = oracle.knn(xyz, xyz, 20, brute=True)
+    assert np.array_equal(out["nn"], nn) and np.all(nn[:, 0] == np.arange(400))  # self is its own nearest neighbour
+    for i in (0, 17, 399):
+        p = xyz[nn[i]]
+        mean = p.astype(np.float64).sum(0) / 20
+        cov = np.zeros((3, 3))
+        for a in range(3):
+            for b in range(a + 1):
+                cov[a, b] = cov[b, a] = (p[:, a] * p[:, b]).astype(np.float32).astype(np.float64).sum() / 20 - mean[a] * mean[b]  # f32 products
+        w, V = np.linalg.eigh(cov)
+        n = V[:, np.argmin(np.abs(w))]
+        C = np.eye(3) - (1 - 1e-3) * np.outer(n, n)
+        assert np.allclose(out["cov"][i], C, atol=1e-7)
+        assert np.allclose(out["dist"][i], np.bincount(labels[nn[i]] - 1, minlength=5) / 20.0, atol=1e-15)
+        assert np.isclose(out["dist"][i].sum(), 1.0, atol=1e-14)
+    assert np.allclose(out["cov"], np.transpose(out["cov"], (0, 2, 1)), atol=0)  # exactly symmetric
+
+
+def test_label_split_first_appearance(oracle):
+    labels = np.array([7, 7, 2, 9, 2, 7, 1, 9], dtype=np.uint32)
+    cl, cs, order = oracle.label_split(labels)
+    assert list(cl) == [7, 2, 9, 1] and list(cs) == [0, 3, 5, 7, 8]
+    assert list(order) == [0, 1, 5, 2, 4, 3, 7, 6]
+
+
+# ------------------------------------------------------------------------------------------------ LM + full aligns
+def test_lm_solve_reaches_scipy_minimiser(oracle, pkg):
+    from scipy.optimize import minimize
+
+    p = pkg.synth.room_pair(seed=3, n_points=600)
+    scov = oracle.covariances(p["src_xyz"], 20, 1e-3)["cov"]
+    tcov = oracle.covariances(p["tgt_xyz"], 20, 1e-3)["cov"]
+    q = oracle.transform_points(p["T_gt"], p["src_xyz"])
+    idx, d2 = oracle.knn(p["tgt_xyz"], q, 1)
+    s_idx, t_idx = np.arange(600), idx[:, 0]
+    x0 = oracle.se3_plus(p["T_gt"], np.array([0.02, -0.01, 0.015, 0.004, -0.003, 0.002]))
+    x, iters, term, cost = oracle.lm_solve(p["src_xyz"], scov, p["tgt_xyz"], tcov, s_idx, t_idx, None, 0, x0)
+    assert term in (2, 3) and iters < 400
+
+    def f(d):
+        return oracle.eval_problem(p["src_xyz"], scov, p["tgt_xyz"], tcov, s_idx, t_idx, None, 0, oracle.se3_plus(x, d))[0]
+
+    res = minimize(f, np.zeros(6), method="Nelder-Mead", options=dict(xatol=1e-9, fatol=1e-14, maxiter=4000))
+    assert res.fun >= cost - 1e-9 * cost          # nothing better nearby
+    c0, g, H = oracle.eval_problem(p["src_xyz"], scov, p["tgt_xyz"], tcov, s_idx, t_idx, None, 0, x)
+    assert np.linalg.norm(np.linalg.solve(H + 1e-12 * np.eye(6), g)) < 1e-5  # Gauss-Newton step at the solution is tiny
+
+
+@pytest.mark.parametrize("algo", ["gicp", "em", "semantic"])
+def test_align_recovers_ground_truth(oracle, pkg, algo):
+    # SemanticICP only uses classes with > 400 source points (semantic_icp.hpp:51): give it enough points per class
+    p = pkg.synth.room_pair(seed=11, n_points=9000 if algo == "semantic" else 3000)
+    if algo == "gicp":
+        r = oracle.align_gicp(p["src_xyz"], p["tgt_xyz"], p["init"])
+    elif algo == "em":
+        r = oracle.align_em(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["init"])
+    else:
+        r = oracle.align_semantic(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["init"])
+    rot, trans = pkg.synth.pose_error(r["pose"], p["T_gt"])
+    assert rot < 5e-3 and trans < 1e-2
+    cap = 36 if algo == "semantic" else 52
+    assert 1 <= r["outer_iter"] <= cap
+    assert np.isclose(np.linalg.norm(r["pose"][:4]), 1.0, atol=1e-12)
+
+
+def test_align_is_thread_count_stable(oracle, pkg):
+    p = pkg.synth.room_pair(seed=12, n_points=1500)
+    a = oracle.align_gicp(p["src_xyz"], p["tgt_xyz"], p["init"], threads=1)
+    b = oracle.align_gicp(p["src_xyz"], p["tgt_xyz"], p["init"], threads=4)
+    rot, trans = pkg.synth.pose_error(a["pose"], b["pose"])
+    assert rot < 1e-8 and trans < 1e-8 and a["outer_iter"] == b["outer_iter"]
+
+
+def test_empty_problem_leaves_pose_unchanged(oracle):
+    src = np.zeros((50, 3), dtype=np.float32) + np.random.default_rng(0).normal(size=(50, 3)).astype(np.float32)
+    tgt = src + np.float32(1000.0)  # every correspondence fails the 250 m^2 gate
+    init = oracle.se3_exp([0.1, 0.2, 0.3, 0.01, 0.02, 0.03])
+    r = oracle.align_gicp(src, tgt, init)
+    assert np.array_equal(r["pose"], init) and r["outer_iter"] == 1 and r["n_corr_last"] == 0
