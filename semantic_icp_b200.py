@@ -21,4 +21,5 @@ def _load(name):
 
 sicp = _load("sicp")
 synth = _load("synth")
+shard = _load("shard")
 PKG_ROOT = os.path.join(_ROOT, "semantic-icp_b200")
