@@ -27,6 +27,7 @@ struct LMConfig {
   int algo;              // SICP_ALGO_*
   int kc;                // correspondences per source point
   double eps;            // PCA epsilon
+  double kappa, hk, k4, aa;  // 1-eps, kappa/2, kappa/4, 1-kappa/2: constant-bank operands of the residual sweep
   int max_iter;          // 400
   double mse_stop;       // 1e-5 (GICP, EM) / 1e-3 (SEMANTIC)
   int outer_cap;         // 50 / 35

@@ -77,9 +77,10 @@ __device__ __forceinline__ void loss_eval(int algo, double w, double s, double* 
 }
 
 // ------------------------------------------------------------------ K3: E-step
-// One thread per candidate pair r = slot*kc + c.  Besides the weight it GATHERS the target point and normal of the
-// pair into residual-ordered arrays, so that the many LM sweeps of the pass stream them with coalesced loads instead
-// of repeating the gather.
+// One thread per candidate pair (slot, c).  Besides the weight it GATHERS the target point and normal of the pair
+// into residual-ordered arrays, so that the many LM sweeps of the pass stream them with coalesced loads instead of
+// repeating the gather.  Gathered arrays are c-major: record (slot, c) lives at c * nslots + slot, so a sweep thread
+// that owns one source slot reads each of its kc records with a fully coalesced warp access.
 __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, double eps, double gate_d2, const double* __restrict__ pose7,
                              const int* __restrict__ stop, int* __restrict__ corr, const float* __restrict__ d2, double* __restrict__ wout,
                              float4* __restrict__ g_pt, double* __restrict__ g_nt, RegCtl* ctl) {
@@ -88,6 +89,7 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
   const int ncorr = sv.nslots * kc;
   const bool live = r < ncorr;
   const int slot = live ? r / kc : 0;
+  const int ro = live ? (r - slot * kc) * sv.nslots + slot : 0;
   int ts = live ? corr[r] : -1;
   double w = 0.0;
   if (ts >= 0 && !((double)d2[r] < gate_d2)) { ts = -1; corr[r] = -1; }  // `distSq < 250` (gicp.hpp:70, em_icp.hpp:65)
@@ -95,8 +97,8 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
     w = 1.0;
     double pt[3], nt[3];
     load_point(tv, ts, pt, nt);
-    g_pt[r] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], 0.f);
-    g_nt[r] = nt[0]; g_nt[(size_t)ncorr + r] = nt[1]; g_nt[2 * (size_t)ncorr + r] = nt[2];
+    g_pt[ro] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], 0.f);
+    g_nt[ro] = nt[0]; g_nt[(size_t)ncorr + ro] = nt[1]; g_nt[2 * (size_t)ncorr + ro] = nt[2];
     if (algo == SICP_ALGO_EM) {
       // label compatibility (em_icp.hpp:84-89) with a_p = CM^T dist_p precomputed per point
       const int N = sv.N;
@@ -124,7 +126,13 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
       w = prob;
     }
   }
-  if (live) wout[r] = w;
+  if (live) {
+    wout[ro] = w;
+    if (ts < 0) {  // no residual: zeroed geometry keeps the branch-free sweep finite (its weight is 0)
+      g_pt[ro] = make_float4(0.f, 0.f, 0.f, 0.f);
+      g_nt[ro] = 0.0; g_nt[(size_t)ncorr + ro] = 0.0; g_nt[2 * (size_t)ncorr + ro] = 0.0;
+    }
+  }
   if (ctl) {  // residual blocks of this pass (diagnostics)
     const int cnt = __popc(__ballot_sync(kFullMask, ts >= 0));
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctl->n_corr_pass, cnt);
@@ -132,10 +140,8 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
 }
 
 // ------------------------------------------------------------------ K4 + K5: LM
-// Solver state of one inner solve.  It lives in global memory (LMSync::state): after every sweep the LAST block to
-// arrive reduces the block partials, runs the LM control step on this state and publishes the next candidate pose;
-// the other blocks wait on a generation flag.  (One atomic + one flag per LM iteration instead of a grid-wide
-// barrier followed by a redundant reduction in every block.)
+// Solver state of one inner solve.  It lives in the shared memory of the controller block (block 0) for the whole
+// launch; LMSync in global memory carries only the arrival counter, the generation flag and the broadcast pose.
 struct LMState {
   double x[7], cand[7];
   double Hs[36], gs[6];        // Jacobi-scaled Gauss-Newton system at x
@@ -149,7 +155,6 @@ struct LMSync {
   unsigned flag;               // generation of the last published control step
   unsigned pad[2];
   double bcast[8];             // candidate pose [7] + done
-  LMState state;
 };
 enum { TERM_NO_CONV = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_RADIUS = 4, TERM_FAIL = 5 };
 
@@ -353,9 +358,9 @@ __device__ __noinline__ void lm_control(LMState& S, const double* tot, int max_i
 struct LMArgs {
   CloudView sv;
   LMConfig cfg;
-  const double* w;          // [ncorr] E-step weights (0 = no residual)
-  const float4* g_pt;       // [ncorr] gathered target points
-  const double* g_nt;       // [3][ncorr] gathered target normals
+  const double* w;          // [kc][nslots] E-step weights (0 = no residual), c-major
+  const float4* g_pt;       // [kc][nslots] gathered target points
+  const double* g_nt;       // [3][kc][nslots] gathered target normals
   RegCtl* ctl;
   double* partials;         // [gridDim.x * kAcc]
   LMSync* sync;
@@ -372,85 +377,186 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Residual sweep at pose x7; leaves this block's 28 partial sums in part[blockIdx.x][:].
+// ---- branch-free FP64 special functions for the sweep.  The library versions carry slow-path subroutine calls for
+// denormal / infinite / negative arguments, which split the residual code into many basic blocks and stop the
+// compiler from interleaving independent residuals; here the arguments are known to be normal and positive
+// (sum >= 1, v >= 2.2e-16, det in (0, 4]), so a MUFU seed + two Newton steps (full double accuracy) is enough.
+__device__ __forceinline__ double rcp_pos(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  return fma(x, e, x);
+}
+__device__ __forceinline__ double rsqrt_pos(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+// log(x) for normal x >= 1 (fdlibm e_log.c reduction and minimax coefficients; error < 1 ulp)
+__device__ __forceinline__ double log_ge1(double x) {
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int k = (hi >> 20) - 1023;
+  hi &= 0x000fffff;
+  const int i = (hi + 0x95f64) & 0x100000;       // mantissa above sqrt(2): halve it, bump the exponent
+  k += i >> 20;
+  const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
+  const double f = m - 1.0;
+  const double sden = rcp_pos(2.0 + f);
+  const double ss = f * sden;
+  const double z = ss * ss;
+  const double w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 + w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)k;
+  // log(1+f) = f - (hfsq - s*(hfsq+R));  log(x) = k*ln2_hi + (log(1+f) + k*ln2_lo)
+  return dk * 6.93147180369123816490e-01 - ((hfsq - (ss * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+
+// rho(s), rho'(s) at s = res^2 of the three Ceres loss compositions, multiplied by the weight w (the
+// E-step weight for EM; exactly 1.0 or 0.0 for GICP / SemanticICP, where 0 marks "no residual in this record").
+template <int ALGO>
+__device__ __forceinline__ void loss_fast(double w, double res, double* rho0, double* rho1) {
+  const double s = res * res;
+  if (ALGO == SICP_ALGO_SEMANTIC) {  // CauchyLoss(1.5)
+    const double sum = 1.0 + s * (1.0 / 2.25);
+    *rho0 = w * (2.25 * log_ge1(sum));
+    *rho1 = w * fmax(DBL_MIN, rcp_pos(sum));
+    return;
+  }
+  // ComposedLoss(CauchyLoss(3.0) [ScaledLoss w for EM], SQLoss): g = sqrt(s + eps), f = 9 log(1 + g/9)
+  const double v = s + DBL_EPSILON;
+  const double rs = rsqrt_pos(v);
+  const double g0 = v * rs;
+  const double sum = 1.0 + g0 * (1.0 / 9.0);
+  const double f0 = w * (9.0 * log_ge1(sum)), f1 = w * fmax(DBL_MIN, rcp_pos(sum));
+  *rho0 = f0;
+  *rho1 = f1 * (0.5 * rs);
+}
+
+// Residual sweep at the pose (P.R, P.t): one thread owns one source slot and its KC gathered records.
+// Everything is evaluated in the TARGET frame so that no per-residual R^T products are needed:
+//   d = p_t - (R p_s + t),  m = R n_s,  b = (2I - kappa(n_t n_t^T + m m^T))^-1 d,  res = d.b
+//   local 6-dof Jacobian of res for T*exp(delta):  J = -2 D j,  j = [b ; v x b],  v = R p_s - kappa (m.b) m,
+//   D = blockdiag(R^T, R^T)                     (equals J_ups = -2c, J_om = 2c x (p_s + C_s c), c = R^T b)
+// The thread accumulates  A_H += rho' j j^T (lower triangle),  A_g += rho' res j,  A_c += rho;  the constant factors
+// (4, -2, 1/2) and the rotation D are applied ONCE to the 28 grid totals by the controller block.
+// The KC records of a slot are evaluated by straight-line, branch-free code (records without a residual have w = 0 and
+// zeroed geometry) so that their dependency chains interleave.
 template <int ALGO, int KC>
-__device__ __forceinline__ void sweep(const LMArgs& a, const double* x7, double (*s_red)[kAcc]) {
-  RT P;
-  quat_to_R(x7, P.R);
-  P.t[0] = x7[4]; P.t[1] = x7[5]; P.t[2] = x7[6];
-  double acc[kAcc];
+__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc) {
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
-  const int ncorr = a.sv.nslots * KC;
-  const double kappa = 1.0 - a.cfg.eps;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < ncorr; r += gridDim.x * blockDim.x) {
-    const double w = __ldg(&a.w[r]);
-    if (w == 0.0) continue;
-    const int slot = r / KC;
+  const int nslots = a.sv.nslots;
+  const size_t ncorr = (size_t)nslots * KC;
+  // Work split: groups of 32 slots (one warp-iteration each).  A block owns a contiguous range of groups and deals
+  // them to its warps round-robin, so the four schedulers of an SM carry the same number of groups (+-1).
+  const int ngroups = nslots >> 5;
+  const int g0 = (int)(((long long)ngroups * blockIdx.x) / gridDim.x), g1 = (int)(((long long)ngroups * (blockIdx.x + 1)) / gridDim.x);
+  const int lane = threadIdx.x & 31;
+  for (int g = g0 + (threadIdx.x >> 5); g < g1; g += kLmThreads / 32) {
+    const int slot = (g << 5) + lane;
+    // every load of the slot is issued before the first use (one L2 round trip per warp-iteration)
+    double w[KC];
+    float4 tp[KC];
+    double u[KC][3];
+#pragma unroll
+    for (int c = 0; c < KC; c++) {
+      const size_t ro = (size_t)c * nslots + slot;
+      w[c] = __ldg(&a.w[ro]);
+      tp[c] = __ldg(&a.g_pt[ro]);
+      u[c][0] = __ldg(&a.g_nt[ro]); u[c][1] = __ldg(&a.g_nt[ncorr + ro]); u[c][2] = __ldg(&a.g_nt[2 * ncorr + ro]);
+    }
     const float4 sp = __ldg(&a.sv.pts[slot]);
-    const float4 tp = __ldg(&a.g_pt[r]);
-    const double ns[3] = {__ldg(&a.sv.nrm[slot]), __ldg(&a.sv.nrm[(size_t)a.sv.nslots + slot]), __ldg(&a.sv.nrm[2 * (size_t)a.sv.nslots + slot])};
-    const double nt[3] = {__ldg(&a.g_nt[r]), __ldg(&a.g_nt[(size_t)ncorr + r]), __ldg(&a.g_nt[2 * (size_t)ncorr + r])};
-    const double ps[3] = {sp.x, sp.y, sp.z};
-    const double pt[3] = {tp.x, tp.y, tp.z};
-    double m[3], d[3];
+    double ns[3] = {__ldg(&a.sv.nrm[slot]), __ldg(&a.sv.nrm[(size_t)nslots + slot]), __ldg(&a.sv.nrm[2 * (size_t)nslots + slot])};
+    bool any = false;
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
-      d[i] = pt[i] - (P.R[3 * i] * ps[0] + P.R[3 * i + 1] * ps[1] + P.R[3 * i + 2] * ps[2] + P.t[i]);
+    for (int c = 0; c < KC; c++) any = any || (w[c] != 0.0);
+    // padding slots hold NaN coordinates and undefined normals; all their weights are 0, so zeroed geometry keeps the
+    // branch-free code below finite (0 * finite = 0) without a divergent skip
+    const double ps[3] = {any ? (double)sp.x : 0.0, any ? (double)sp.y : 0.0, any ? (double)sp.z : 0.0};
+#pragma unroll
+    for (int i = 0; i < 3; i++) ns[i] = any ? ns[i] : 0.0;
+    double q0[3], qt[3], m[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {  // R, t are read from shared memory (broadcast) instead of pinning 24 registers
+      const double r0 = s_RT[3 * i], r1 = s_RT[3 * i + 1], r2 = s_RT[3 * i + 2];
+      q0[i] = r0 * ps[0] + r1 * ps[1] + r2 * ps[2];
+      qt[i] = q0[i] + s_RT[9 + i];
+      m[i] = r0 * ns[0] + r1 * ns[1] + r2 * ns[2];
     }
-    double b[3];
-    apply_Minv(nt, m, d, kappa, b);
-    const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
-    double rho0, rho1;
-    loss_eval(ALGO, w, res * res, &rho0, &rho1);
-    acc[27] += 0.5 * rho0;
-    double c[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) c[i] = P.R[i] * b[0] + P.R[3 + i] * b[1] + P.R[6 + i] * b[2];  // R^T b
-    const double nc = kappa * (ns[0] * c[0] + ns[1] * c[1] + ns[2] * c[2]);
-    const double e[3] = {ps[0] + c[0] - nc * ns[0], ps[1] + c[1] - nc * ns[1], ps[2] + c[2] - nc * ns[2]};  // p_s + C_s c
-    const double sr = sqrt(rho1);
-    const double s2 = 2.0 * sr;
-    double J[6];
-    J[0] = -s2 * c[0]; J[1] = -s2 * c[1]; J[2] = -s2 * c[2];
-    J[3] = s2 * (c[1] * e[2] - c[2] * e[1]);
-    J[4] = s2 * (c[2] * e[0] - c[0] * e[2]);
-    J[5] = s2 * (c[0] * e[1] - c[1] * e[0]);
-    const double rc = sr * res;
-    int k = 0;
+    for (int c = 0; c < KC; c++) {
+      const double d[3] = {(double)tp[c].x - qt[0], (double)tp[c].y - qt[1], (double)tp[c].z - qt[2]};
+      // b = M d (rank-2 Woodbury, see apply_Minv)
+      const double cuv = u[c][0] * m[0] + u[c][1] * m[1] + u[c][2] * m[2];
+      const double pu = u[c][0] * d[0] + u[c][1] * d[1] + u[c][2] * d[2];
+      const double pm = m[0] * d[0] + m[1] * d[1] + m[2] * d[2];
+      const double be = a.cfg.hk * cuv;
+      const double idet = a.cfg.k4 * rcp_pos((a.cfg.aa - be) * (a.cfg.aa + be));
+      const double g1c = (a.cfg.aa * pu + be * pm) * idet, g2c = (be * pu + a.cfg.aa * pm) * idet;
+      double b[3];
 #pragma unroll
-    for (int p = 0; p < 6; p++) {
+      for (int i = 0; i < 3; i++) b[i] = 0.5 * d[i] + (g1c * u[c][i] + g2c * m[i]);
+      const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
+      double rho0, rho1;
+      loss_fast<ALGO>(w[c], res, &rho0, &rho1);
+      const double mb = a.cfg.kappa * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]);
+      const double v[3] = {q0[0] - mb * m[0], q0[1] - mb * m[1], q0[2] - mb * m[2]};
+      double j[6], jw[6];
+      j[0] = b[0]; j[1] = b[1]; j[2] = b[2];
+      j[3] = v[1] * b[2] - v[2] * b[1];
+      j[4] = v[2] * b[0] - v[0] * b[2];
+      j[5] = v[0] * b[1] - v[1] * b[0];
 #pragma unroll
-      for (int q = 0; q <= p; q++) acc[k++] += J[p] * J[q];
-      acc[21 + p] += J[p] * rc;
+      for (int p = 0; p < 6; p++) jw[p] = rho1 * j[p];
+      int k = 0;
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+#pragma unroll
+        for (int q = 0; q <= p; q++) acc[k++] += jw[p] * j[q];
+        acc[21 + p] += jw[p] * res;
+      }
+      acc[27] += rho0;
     }
-  }
-  // warp butterfly (fixed order => deterministic), then a fixed-order block sum
-#pragma unroll
-  for (int i = 0; i < kAcc; i++)
-    for (int o = 16; o; o >>= 1) acc[i] += __shfl_xor_sync(kFullMask, acc[i], o);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();  // s_red may still be read by the previous round
-  if (lane == 0)
-#pragma unroll
-    for (int i = 0; i < kAcc; i++) s_red[warp][i] = acc[i];
-  __syncthreads();
-  if (threadIdx.x < kAcc) {
-    double s = 0;
-#pragma unroll
-    for (int wv = 0; wv < kLmThreads / 32; wv++) s += s_red[wv][threadIdx.x];
-    a.partials[(size_t)blockIdx.x * kAcc + threadIdx.x] = s;
   }
 }
 
-// Fixed-order sum of the block partials (done by one block): warp `sub` sums blocks sub, sub+8, ... with independent
-// loads, then the 8 warp sums are added in order.  Result in s_tot[0..27].
+// Block reduction of the 28 per-thread sums through shared memory (fixed order => deterministic): every thread
+// stores its 28 values, then 28 x 8 threads each add one 32-value segment of one row (rotated start: conflict-free)
+// and a 3-step butterfly joins the 8 segments.  Leaves the block's sums in part[blockIdx.x][0..27].
+__device__ __forceinline__ void block_reduce(const double* acc, double* s_acc, double* part) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < kAcc; i++) s_acc[i * kLmThreads + tid] = acc[i];
+  __syncthreads();
+  if (tid < kAcc * 8) {
+    const int row = tid >> 3, seg = tid & 7;
+    const double* base = s_acc + row * kLmThreads + seg * 32;
+    double s = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) s += base[(k + tid) & 31];
+    s += __shfl_xor_sync(kFullMask, s, 1);
+    s += __shfl_xor_sync(kFullMask, s, 2);
+    s += __shfl_xor_sync(kFullMask, s, 4);
+    if (seg == 0) part[(size_t)blockIdx.x * kAcc + row] = s;
+  }
+}
+
+// Fixed-order sum of the block partials by the controller block: warp `sub` sums blocks sub, sub+8, ... with
+// independent loads, then the 8 warp sums are added in order.  Result in s_tot[0..27].
 __device__ __forceinline__ void reduce_partials(const double* part, double (*s_red)[kAcc], double* s_tot) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0;
   if (lane < kAcc) {
-    // up to kMaxPerWarp independent loads in flight per lane (one L2 round trip), then the fixed-order sum
     constexpr int kMaxPerWarp = 40;  // grids of up to 320 blocks
     double v[kMaxPerWarp];
 #pragma unroll
@@ -461,7 +567,6 @@ __device__ __forceinline__ void reduce_partials(const double* part, double (*s_r
 #pragma unroll
     for (int k = 0; k < kMaxPerWarp; k++) s += v[k];
   }
-  __syncthreads();
   if (lane < kAcc) s_red[warp][lane] = s;
   __syncthreads();
   if (threadIdx.x < kAcc) {
@@ -473,60 +578,101 @@ __device__ __forceinline__ void reduce_partials(const double* part, double (*s_r
   __syncthreads();
 }
 
+// Grid totals (A_H, A_g, A_c) -> Ceres quantities in the local frame of the evaluated pose:
+//   H = 4 D A_H D^T,  g = -2 D A_g,  cost = A_c / 2,  D = blockdiag(R^T, R^T).  28 threads, one output each.
+__device__ __forceinline__ void rotate_totals(const double* s_tot, const double* R, double* s_rot) {
+  const int e = threadIdx.x;
+  if (e < 21) {
+    int a = 0;
+    while ((a + 1) * (a + 2) / 2 <= e) a++;
+    const int b = e - a * (a + 1) / 2;
+    const int A = a / 3, i = a % 3, B = b / 3, jx = b % 3;
+    double s = 0;
+    for (int k = 0; k < 3; k++)
+      for (int l = 0; l < 3; l++) s += R[3 * k + i] * s_tot[tri(3 * A + k, 3 * B + l)] * R[3 * l + jx];
+    s_rot[e] = 4.0 * s;
+  } else if (e < 27) {
+    const int a = e - 21, A = a / 3, i = a % 3;
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += R[3 * k + i] * s_tot[21 + 3 * A + k];
+    s_rot[e] = -2.0 * s;
+  } else if (e == 27) {
+    s_rot[27] = 0.5 * s_tot[27];
+  }
+}
+
+// One inner solve (+ the outer-loop test) per launch.  Block 0 is the CONTROLLER: after every sweep the other blocks
+// signal arrival on a counter and wait on a generation flag; block 0 waits for the counter, sums the block partials,
+// runs the LM control step on solver state that stays in ITS shared memory for the whole solve, and publishes the next
+// pose.  One atomic + one flag per LM iteration; no grid-wide barrier, no state traffic through global memory.
 template <int ALGO, int KC>
 __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
+  extern __shared__ double s_acc[];  // [kAcc][kLmThreads]
   __shared__ LMState S;
   __shared__ double s_red[kLmThreads / 32][kAcc];
   __shared__ double s_tot[kAcc];
+  __shared__ double s_rot[kAcc];
   __shared__ double s_x[8];  // pose to evaluate [7] + done flag
-  __shared__ int s_last;
-  constexpr int kStateWords = (int)(sizeof(LMState) / sizeof(double));
-  static_assert(sizeof(LMState) % sizeof(double) == 0, "LMState must be a whole number of doubles");
+  __shared__ double s_RT[12];  // its rotation matrix (row-major) and translation
   LMSync* sy = a.sync;
   const bool eval_only = a.eval_pose != nullptr;
+  const bool controller = blockIdx.x == 0;
   if (threadIdx.x < 7) s_x[threadIdx.x] = eval_only ? a.eval_pose[threadIdx.x] : a.ctl->pose[threadIdx.x];
   if (threadIdx.x == 7) s_x[7] = eval_only ? 0.0 : (double)a.ctl->converged;
+  if (controller && threadIdx.x == 0) S.started = 0;
   __syncthreads();
   if (s_x[7] != 0.0) return;  // registration already converged: passes enqueued ahead of the host return at once
-  const unsigned gen0 = ld_acquire(&sy->flag);  // generations continue across launches
-  unsigned gen = gen0;
-  long long t_comp = 0, t_ctl = 0, t_wait = 0, t_red = 0, t_ld = 0, t_lm = 0;
+  unsigned gen = ld_acquire(&sy->flag);  // generations continue across launches
+  long long t_comp = 0, t_ctl = 0, t_wait = 0, t_red = 0, t_lm = 0;
   const long long t_start = clock64();
   for (;;) {
     long long t0 = clock64();
-    sweep<ALGO, KC>(a, s_x, s_red);
+    if (threadIdx.x == 0) {
+      quat_to_R(s_x, s_RT);
+      s_RT[9] = s_x[4]; s_RT[10] = s_x[5]; s_RT[11] = s_x[6];
+    }
+    __syncthreads();
+    double acc[kAcc];
+    sweep_acc<ALGO, KC>(a, s_RT, acc);
+    block_reduce(acc, s_acc, a.partials);
     gen++;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&sy->count, 1u) == gridDim.x - 1);
-    __syncthreads();
     t_comp += clock64() - t0;
     t0 = clock64();
-    if (s_last) {
-      __threadfence();
+    if (!controller) {
+      if (threadIdx.x == 0) {
+        atomicAdd(&sy->count, 1u);
+        if (!eval_only) while ((int)(ld_acquire(&sy->flag) - gen) < 0) __nanosleep(32);
+      }
+      if (eval_only) return;
+      __syncthreads();
+      if (threadIdx.x < 8) s_x[threadIdx.x] = __ldcg(&sy->bcast[threadIdx.x]);
+      __syncthreads();
+      t_wait += clock64() - t0;
+    } else {
+      if (threadIdx.x == 0) while (ld_acquire(&sy->count) != gridDim.x - 1) { }
+      __syncthreads();
+      t_wait += clock64() - t0;
+      t0 = clock64();
       reduce_partials(a.partials, s_red, s_tot);
+      rotate_totals(s_tot, s_RT, s_rot);
+      __syncthreads();
       const long long t1 = clock64();
       t_red += t1 - t0;
       if (eval_only) {
-        if (threadIdx.x < kAcc) a.eval_out[threadIdx.x] = s_tot[threadIdx.x];
-        if (threadIdx.x == 0) { sy->bcast[7] = 1.0; sy->count = 0; __threadfence(); st_release(&sy->flag, gen); }
+        if (threadIdx.x < kAcc) a.eval_out[threadIdx.x] = s_rot[threadIdx.x];
+        if (threadIdx.x == 0) sy->count = 0;
         return;
       }
-      // bring the solver state in, run the control step, publish
-      double* gs = reinterpret_cast<double*>(&sy->state);
-      double* ss = reinterpret_cast<double*>(&S);
-      const bool first = (gen == gen0 + 1);
-      if (!first) for (int i = threadIdx.x; i < kStateWords; i += blockDim.x) ss[i] = __ldcg(&gs[i]);
-      __syncthreads();
-      const long long t2 = clock64();
-      t_ld += t2 - t1;
       if (threadIdx.x == 0) {
-        if (first) {
-          for (int i = 0; i < kStateWords; i++) ss[i] = 0.0;
+        if (!S.started) {
+          double* ss = reinterpret_cast<double*>(&S);
+          for (int i = 0; i < (int)(sizeof(LMState) / sizeof(double)); i++) ss[i] = 0.0;
           for (int i = 0; i < 7; i++) S.x[i] = s_x[i];
         }
-        lm_control(S, s_tot, a.cfg.max_iter);
-        t_lm += clock64() - t2;
+        lm_control(S, s_rot, a.cfg.max_iter);
+        t_lm += clock64() - t1;
         if (S.done) {
           // outer-loop bookkeeping: mse = |log(cur^-1 est)|^2 (impl/gicp.hpp:153), stop rule, pass trace
           RegCtl* c = a.ctl;
@@ -551,38 +697,25 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
           if (conv && !(mse < a.cfg.mse_stop)) c->flags |= 1;
           c->converged = conv ? 1 : 0;
         }
-        for (int i = 0; i < 7; i++) sy->bcast[i] = S.cand[i];
-        sy->bcast[7] = S.done ? 1.0 : 0.0;
+        for (int i = 0; i < 7; i++) { s_x[i] = S.cand[i]; sy->bcast[i] = S.cand[i]; }
+        s_x[7] = S.done ? 1.0 : 0.0;
+        sy->bcast[7] = s_x[7];
         sy->count = 0;
+        __threadfence();
+        st_release(&sy->flag, gen);
       }
       __syncthreads();
-      if (!S.done) for (int i = threadIdx.x; i < kStateWords; i += blockDim.x) gs[i] = ss[i];
-      __threadfence();
-      __syncthreads();
-      if (threadIdx.x == 0) st_release(&sy->flag, gen);
       t_ctl += clock64() - t0;
-    } else {
-      if (threadIdx.x == 0) while ((int)(ld_acquire(&sy->flag) - gen) < 0) __nanosleep(32);
-      __syncthreads();
-      t_wait += clock64() - t0;
     }
-    if (eval_only) return;
-    if (threadIdx.x < 8) s_x[threadIdx.x] = __ldcg(&sy->bcast[threadIdx.x]);
-    __syncthreads();
     if (s_x[7] != 0.0) break;
   }
-  if (threadIdx.x == 0) {  // diagnostics: block 0's sweep / wait cycles, everybody's control cycles (only the last arrivals have any)
-    if (blockIdx.x == 0) {
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[0], (unsigned long long)t_comp);
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[1], (unsigned long long)t_wait);
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[3], (unsigned long long)(clock64() - t_start));
-    }
-    if (t_ctl) {
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[2], (unsigned long long)t_ctl);
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[4], (unsigned long long)t_red);
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[5], (unsigned long long)t_ld);
-      atomicAdd((unsigned long long*)&a.ctl->dbg_cycles[6], (unsigned long long)t_lm);
-    }
+  if (threadIdx.x == 0 && controller) {  // diagnostics: controller block's sweep / wait / control cycles
+    a.ctl->dbg_cycles[0] += t_comp;
+    a.ctl->dbg_cycles[1] += t_wait;
+    a.ctl->dbg_cycles[2] += t_ctl;
+    a.ctl->dbg_cycles[3] += clock64() - t_start;
+    a.ctl->dbg_cycles[4] += t_red;
+    a.ctl->dbg_cycles[6] += t_lm;
   }
 }
 
@@ -638,12 +771,15 @@ static void* lm_entry(int algo) {
     default: return (void*)lm_kernel<SICP_ALGO_EM, 4>;
   }
 }
+constexpr size_t kLmSmem = sizeof(double) * kAcc * kLmThreads;  // block_reduce staging (56 KB, opt-in dynamic shared memory)
 int lm_grid_blocks(int device) {
   static int cached[64] = {0};
   if (device >= 0 && device < 64 && cached[device]) return cached[device];
   int sms = 148, per_sm = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_kernel<SICP_ALGO_EM, 4>, kLmThreads, 0);
+  for (int algo : {SICP_ALGO_GICP, SICP_ALGO_SEMANTIC, SICP_ALGO_EM})
+    cudaFuncSetAttribute(lm_entry(algo), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmSmem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_kernel<SICP_ALGO_EM, 4>, kLmThreads, kLmSmem);
   if (per_sm < 1) per_sm = 1;
   int g = sms * std::min(per_sm, 2);
   if (device >= 0 && device < 64) cached[device] = g;
@@ -664,7 +800,7 @@ sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMC
 
 static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
   void* params[] = {&args};
-  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo), dim3(grid), dim3(kLmThreads), params, 0, st));
+  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo), dim3(grid), dim3(kLmThreads), params, kLmSmem, st));
   count_launches(1);
   return SICP_OK;
 }
@@ -672,7 +808,7 @@ static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
 sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt, RegCtl* d_ctl,
                       double* d_partials, int grid, cudaStream_t st) {
   LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, d_ctl, d_partials + (size_t)grid * kAcc, reinterpret_cast<LMSync*>(d_partials), nullptr, nullptr};
-  static_assert(sizeof(LMSync) <= sizeof(double) * 148 * kAcc, "LMSync must fit in the first partials slab");
+  static_assert(sizeof(LMSync) <= sizeof(double) * kAcc, "LMSync must fit in the first partials slab");
   return launch_lm_args(args, grid, st);
 }
 

@@ -16,6 +16,7 @@ static LMConfig make_cfg(int algo, const sicp_options& o) {
   c.algo = algo;
   c.kc = algo == SICP_ALGO_EM ? 4 : 1;                      // em_icp.hpp:60 / gicp.hpp:69, semantic_icp.hpp:68
   c.eps = o.epsilon;
+  c.kappa = 1.0 - o.epsilon; c.hk = 0.5 * c.kappa; c.k4 = 0.25 * c.kappa; c.aa = 1.0 - c.hk;
   c.max_iter = o.max_lm_iterations;
   c.mse_stop = algo == SICP_ALGO_SEMANTIC ? 1e-3 : 1e-5;    // semantic_icp.hpp:152 / gicp.hpp:154, em_icp.hpp:180
   c.outer_cap = algo == SICP_ALGO_SEMANTIC ? 35 : 50;
@@ -334,7 +335,7 @@ sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, con
       int to = -1;
       if (ts >= 0) std::memcpy(&to, &h_tpts[ts].w, 4);
       idx_out[(size_t)o * cfg.kc + c] = to;
-      if (w_out) w_out[(size_t)o * cfg.kc + c] = h_w[(size_t)s * cfg.kc + c];
+      if (w_out) w_out[(size_t)o * cfg.kc + c] = h_w[(size_t)c * src->nslots + s];  // gathered arrays are c-major
       if (d2_out) d2_out[(size_t)o * cfg.kc + c] = h_d2[(size_t)s * cfg.kc + c];
     }
   }
