@@ -227,12 +227,8 @@ def main():
     clocks = sampler.summary() if sampler else None
     ms_e2e, res_e2e, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
 
-    # pose gather: the only collective on this path (tiny payload, after the timed region)
-    poses = torch.tensor(np.stack([r["pose"] for r in res_dev]), device=dev)
-    if world > 1:
-        allp = [torch.empty_like(poses) for _ in range(world)]
-        dist.all_gather(allp, poses)
-        poses = torch.cat(allp)
+    # result gather: the only collective on this path — one all_gather of 96-byte records, after the timed region
+    records = pkg.shard.gather_records(pkg.shard.to_records(res_dev), [B] * world, device=dev)
 
     if rank == 0:
         total_pairs = B * world
@@ -271,8 +267,29 @@ def main():
                     "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": round(kernels[dom]["ms_total"] / max(1, launches_per_unit[dom]), 4),
                     "alg_bytes_per_launch": kernels[dom]["alg_bytes"] / max(1, launches_per_unit[dom]),
+                    "measured_on": "per-stage CUDA events (launching stream) of one profiled registration run inside bench.py after the timed region; "
+                                   "stages of concurrent registrations overlap in the batch itself",
                     "note": "working set of one pair is L2-resident; DRAM traffic is far below algorithmic bytes (see profiles/)",
                     "kernels": kernels}
+        # secondary metric of BASELINE.json: exact kNN queries/s (120k transformed source points against the 120k target tree)
+        knn_qps = {}
+        s = sicp.Cloud(p0["src_xyz"], p0["src_labels"], device=local_rank)
+        t = sicp.Cloud(p0["tgt_xyz"], p0["tgt_labels"], device=local_rank)
+        for k in (1, 4, 20):
+            o_idx = torch.empty(n * k, dtype=torch.int32, device=dev)
+            o_d2 = torch.empty(n * k, dtype=torch.float32, device=dev)
+            for _ in range(3):
+                sicp.knn_cloud(t, s, k, o_idx.data_ptr(), o_d2.data_ptr(), pose7=p0["T_gt"])
+            torch.cuda.synchronize()
+            reps = 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                sicp.knn_cloud(t, s, k, o_idx.data_ptr(), o_d2.data_ptr(), pose7=p0["T_gt"])
+            e1.record()
+            e1.synchronize()
+            knn_qps[f"k{k}"] = n * reps / (e0.elapsed_time(e1) * 1e-3)
+        s.close(); t.close()
         cpu = None
         if not args.no_cpu_baseline:
             r, cores = cpu_oracle_run(p0)
@@ -293,7 +310,7 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "poses_gathered": int(poses.shape[0]),
+            "records_gathered": int(records.shape[0]), "knn_queries_per_s": knn_qps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -48,9 +48,7 @@ void pinned_release(PinnedBlock& b, cudaStream_t st) {  // call after the last c
   g_pin_pool.push_back(b);
 }
 
-// ---- bounding box: block reduce + ordered-int atomics -------------------------------------------------------
-__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+// ---- bounding box: block reduce + ordered-int atomics (f2ord / ord2f / morton30 live in knn.cuh) --------------------
 
 // bb[0..5] = ordered-int min/max of xyz; bb[6], bb[7] = min/max label
 __global__ void bbox_init_kernel(int* bb) {
@@ -85,29 +83,13 @@ __global__ void bbox_kernel(const float* __restrict__ xyz, const uint32_t* __res
     if ((threadIdx.x & 31) == 0) { atomicMin((unsigned*)&bb[6], llo); atomicMax((unsigned*)&bb[7], lhi); }
   }
 }
-// 30-bit Morton code (10 bits per axis) in the cloud's bounding cube; PER_CLASS clouds put the class rank above it
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {
-  v &= 0x3ff;
-  v = (v | (v << 16)) & 0x030000ff;
-  v = (v | (v << 8)) & 0x0300f00f;
-  v = (v | (v << 4)) & 0x030c30c3;
-  v = (v | (v << 2)) & 0x09249249;
-  return v;
-}
+// 30-bit Morton code in the cloud's bounding cube (morton30, knn.cuh); PER_CLASS clouds put the class rank above it
 template <typename KeyT>
 __global__ void key_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rank, int n, const int* __restrict__ bb, KeyT* keys,
                            uint32_t* vals) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float lo[3], ext = 0.f;
-  for (int c = 0; c < 3; c++) { lo[c] = ord2f(bb[c]); ext = fmaxf(ext, ord2f(bb[3 + c]) - lo[c]); }
-  if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
-  const float inv_cell = 1023.f / ext;
-  uint32_t m = 0;
-  for (int c = 0; c < 3; c++) {
-    const float f = fminf(fmaxf((xyz[3 * (size_t)i + c] - lo[c]) * inv_cell, 0.f), 1023.f);
-    m |= spread10((uint32_t)f) << c;
-  }
+  const uint32_t m = morton30(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], bb);
   KeyT k = m;
   if (sizeof(KeyT) == 8 && rank) k |= (KeyT)((uint64_t)rank[i] << 32);
   keys[i] = k;
@@ -141,7 +123,7 @@ __global__ void slot_kernel(const float* __restrict__ xyz, const uint32_t* __res
 }
 // level 0: one warp per leaf
 __global__ void leaf_box_kernel(const float4* __restrict__ pts, const int* __restrict__ seg_of_leaf, const Segment* __restrict__ seg,
-                                int nleaf, float4* node_lo, float4* node_hi) {
+                                int nleaf, const int* __restrict__ bb, float4* node_lo, float4* node_hi, uint32_t* leaf_key) {
   const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
   if (leaf >= nleaf) return;
   const float4 p = pts[(size_t)leaf * kLeaf + (threadIdx.x & 31)];
@@ -156,6 +138,7 @@ __global__ void leaf_box_kernel(const float4* __restrict__ pts, const int* __res
     const int li = sg.node_off[0] + (leaf - sg.leaf0);
     node_lo[li] = make_float4(lo[0], lo[1], lo[2], 0.f);
     node_hi[li] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    leaf_key[leaf] = morton30(p.x, p.y, p.z, bb);  // lane 0 holds the leaf's first (never padding) point
   }
 }
 // upper levels: one block per segment, levels separated by __syncthreads
@@ -216,12 +199,13 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
   auto carve = [&](size_t bytes) { size_t o = off; off += align256(std::max<size_t>(bytes, 16)); return o; };
   const size_t o_pts = carve(sizeof(float4) * c->nslots), o_lab = carve(sizeof(uint32_t) * c->nslots), o_sol = carve(sizeof(int) * c->nleaf),
                o_seg = carve(sizeof(Segment) * nseg), o_nlo = carve(sizeof(float4) * c->nnodes), o_nhi = carve(sizeof(float4) * c->nnodes),
-               o_soo = carve(sizeof(int) * n), o_bb = carve(sizeof(int) * 8);
+               o_soo = carve(sizeof(int) * n), o_bb = carve(sizeof(int) * 8), o_lk = carve(sizeof(uint32_t) * c->nleaf);
   SICP_CUDA(cudaMallocAsync(&c->d_slab, off, st));
   char* base = (char*)c->d_slab;
   c->d_pts = (float4*)(base + o_pts); c->d_label = (uint32_t*)(base + o_lab); c->d_seg_of_leaf = (int*)(base + o_sol);
   c->d_seg = (Segment*)(base + o_seg); c->d_node_lo = (float4*)(base + o_nlo); c->d_node_hi = (float4*)(base + o_nhi);
   c->d_slot_of_orig = (int*)(base + o_soo); c->d_bb = (int*)(base + o_bb);
+  c->d_leaf_key = (uint32_t*)(base + o_lk);
 
   PinnedBlock pb;
   void* stage = pinned_stage(sizeof(Segment) * std::max(1, nseg), st, &pb);
@@ -258,7 +242,7 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
   else seg_of_leaf_kernel<<<(c->nleaf + T - 1) / T, T, 0, st>>>(c->d_seg, nseg, c->nleaf, c->d_seg_of_leaf);
   slot_kernel<<<(c->nslots + T - 1) / T, T, 0, st>>>(d_xyz, d_labels, vals2, c->d_seg_of_leaf, c->d_seg, c->nslots, c->d_pts, c->d_label,
                                                      c->d_slot_of_orig);
-  leaf_box_kernel<<<(c->nleaf * 32 + T - 1) / T, T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_node_lo, c->d_node_hi);
+  leaf_box_kernel<<<(c->nleaf * 32 + T - 1) / T, T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_bb, c->d_node_lo, c->d_node_hi, c->d_leaf_key);
   upper_box_kernel<<<nseg, 256, 0, st>>>(c->d_seg, c->d_node_lo, c->d_node_hi);
   count_launches(6 + (nseg > 1) + ((wide ? 39 : 30) + 7) / 8 + 2);  // own kernels + CUB onesweep (histogram, scan, one pass per 8 key bits)
   SICP_CUDA(cudaGetLastError());
@@ -314,7 +298,7 @@ sicp::CloudView sicp_cloud::view() const {
   CloudView v;
   v.n = (int)n; v.nslots = nslots; v.nseg = nseg;
   v.pts = d_pts; v.label = d_label; v.seg_of_leaf = d_seg_of_leaf; v.seg = d_seg;
-  v.node_lo = d_node_lo; v.node_hi = d_node_hi;
+  v.node_lo = d_node_lo; v.node_hi = d_node_hi; v.leaf_key = d_leaf_key; v.bb = d_bb;
   v.nrm = d_nrm; v.avec = d_avec; v.N = pre_N;
   return v;
 }

@@ -71,6 +71,8 @@ struct CloudView {
   const Segment* seg;    // [nseg]
   const float4* node_lo; // node boxes, all segments / levels
   const float4* node_hi;
+  const uint32_t* leaf_key; // [nleaf_total] 30-bit Morton code of each leaf's first point (ascending inside a segment)
+  const int* bb;            // [8] ordered-int bounding box of the cloud (the Morton quantisation frame)
   const double* nrm;     // [3*nslots] SoA normals nx | ny | nz  (after precompute)
   const double* avec;    // [nslots*N] label vectors a_p = CM^T dist_p (EM)
   int N;
@@ -95,6 +97,7 @@ struct sicp_cloud {
   float4* d_node_lo = nullptr;
   float4* d_node_hi = nullptr;
   int* d_slot_of_orig = nullptr;  // [n] inverse permutation
+  uint32_t* d_leaf_key = nullptr; // [nleaf]
   double* d_nrm = nullptr;
   double* d_avec = nullptr;
   // precompute cache key

@@ -18,7 +18,37 @@
 namespace sicp {
 
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kStackCap = 8 * kMaxLevels;             // DFS over an 8-ary tree: <= 7 pending siblings per level
+constexpr int kMaxSeed = 24;                           // seed leaves injected before the traversal (see knn_search)
+constexpr int kStackCap = 8 * kMaxLevels + kMaxSeed;   // DFS over an 8-ary tree: <= 7 pending siblings per level, plus the seeds
+constexpr int kForced = 1 << 25;                       // stack entry flag: seed leaf (nleaf < 2^25)
+
+// ---- Morton quantisation shared by the build (cloud.cu) and the query-side home-leaf lookup
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v &= 0x3ff;
+  v = (v | (v << 16)) & 0x030000ff;
+  v = (v | (v << 8)) & 0x0300f00f;
+  v = (v | (v << 4)) & 0x030c30c3;
+  v = (v | (v << 2)) & 0x09249249;
+  return v;
+}
+// 30-bit Morton code (10 bits per axis) of (x,y,z) in the bounding cube described by bb (ordered ints, see bbox_kernel)
+__device__ __forceinline__ uint32_t morton30(float x, float y, float z, const int* __restrict__ bb) {
+  float lo[3], ext = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; c++) { lo[c] = ord2f(bb[c]); ext = fmaxf(ext, ord2f(bb[3 + c]) - lo[c]); }
+  if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
+  const float inv_cell = 1023.f / ext;
+  const float p[3] = {x, y, z};
+  uint32_t m = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const float f = fminf(fmaxf((p[c] - lo[c]) * inv_cell, 0.f), 1023.f);
+    m |= spread10((uint32_t)f) << c;
+  }
+  return m;
+}
 
 #ifdef SICP_STATS
 static __device__ unsigned long long g_stats[8];  // per warp: 0 node expansions, 1 leaf scans, 3 phase-2 iterations; per lane: 2 insertions
@@ -75,7 +105,25 @@ struct WarpScratch {
   int2 stack[kStackCap];     // x = level << 26 | idx, y = key bits (min box distance over the lanes)
 };
 
+// Leaf of segment `sg` whose Morton range contains the query (last leaf whose first key is <= the query's key).
+__device__ __forceinline__ int home_leaf(const CloudView& tv, const Segment& sg, float qx, float qy, float qz) {
+  const uint32_t key = morton30(qx, qy, qz, tv.bb);
+  const uint32_t* lk = tv.leaf_key + sg.leaf0;
+  int lo = 0, hi = sg.nleaf - 1;  // invariant: answer in [lo, hi]
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&lk[mid]) <= key) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 // Packet search of one warp's 32 queries in segment `sg` (warp-uniform).  Exact for every valid lane.
+//
+// Seeding: a plain nearest-first descent gives good bounds only to the lanes closest to the first leaves; the others
+// keep loose bounds for many scans ("needing" most leaves they meet).  So before the traversal every lane looks up its
+// HOME leaf (Morton binary search) and the distinct home leaves of the packet (+- SEED Morton neighbours) are pushed on
+// top of the stack: they are scanned first, after which every lane's k-th bound is already close to final.  Seed leaves
+// are remembered (one per lane register) and skipped when the traversal reaches them again.
 template <int K>
 __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& sg, float qx, float qy, float qz, bool valid, TopK<K>& L,
                                            WarpScratch& ws) {
@@ -83,6 +131,10 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
   const int lane = threadIdx.x & 31;
   const int top = sg.nlevels - 1;
   int sp = 0;
+  constexpr int SEED = (K >= 8) ? 1 : 0;
+  const int home = valid ? home_leaf(tv, sg, qx, qy, qz) : -1;
+  int myseed = -1;   // lane i remembers the i-th seed leaf
+  bool seeded = false;
   // virtual root: expand the top level (<= kArity nodes); afterwards pop / expand / scan
   int level = top + 1, idx = 0;
   for (;;) {
@@ -117,6 +169,25 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       sp += m;
       SICP_STAT(0, 1);
       __syncwarp();
+      if (!seeded) {  // right after the virtual-root expansion: seed leaves go on top of the stack
+        seeded = true;
+        unsigned pending = __ballot_sync(kFull, home >= 0);
+        int nseed = 0;
+        while (pending && nseed + 2 * SEED + 1 <= kMaxSeed) {
+          const int h = __shfl_sync(kFull, home, __ffs(pending) - 1);
+#pragma unroll
+          for (int dl = SEED; dl >= -SEED; dl--) {
+            const int lf = h + dl;
+            if (lf < 0 || lf >= sg.nleaf) continue;
+            if (__any_sync(kFull, myseed == lf)) continue;
+            if (lane == nseed) myseed = lf;
+            if (lane == 0) ws.stack[sp] = make_int2(kForced | lf, 0);
+            nseed++; sp++;
+          }
+          pending &= ~__ballot_sync(kFull, home == h);
+        }
+        __syncwarp();
+      }
     } else {
       // ---- leaf: stage 32 candidates through shared memory, every lane scans all of them
       const int slot0 = sg.p0 + idx * kLeaf;
@@ -156,12 +227,17 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       const float wmax = __uint_as_float(__reduce_max_sync(kFull, valid ? __float_as_uint(L.worst()) : 0u));
       if (__int_as_float(e.y) > wmax) continue;
       level = e.x >> 26;
-      idx = e.x & ((1 << 26) - 1);
+      idx = e.x & (kForced - 1);
       if (level == 0) {  // exact per-lane re-test of the leaf box before paying for the scan
+        if (!(e.x & kForced) && __any_sync(kFull, myseed == idx)) continue;  // already scanned as a seed
         const int ni = sg.node_off[0] + idx;
         const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
         const float lb = box_lb_rn(qx, qy, qz, lo, hi);
-        if (!__any_sync(kFull, valid && !(lb > L.worst()))) continue;
+        const unsigned needers = __ballot_sync(kFull, valid && !(lb > L.worst()));
+        if (!needers) continue;
+        SICP_STAT(4, __popc(needers));
+        SICP_STAT(5, __popc(needers) <= 8 ? 1 : 0);
+        SICP_STAT(6, __popc(needers) <= 16 ? 1 : 0);
       }
       found = true;
       break;

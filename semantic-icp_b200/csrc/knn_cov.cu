@@ -494,9 +494,14 @@ sicp_status sicp_knn_cloud(const sicp_cloud* tgt, const sicp_cloud* q, const dou
   int* d_map = nullptr;
   SICP_CHECK(make_class_map(q, tgt, -1, &d_map, st));
   double* d_pose = nullptr;
-  if (pose7) {
+  if (pose7) {  // staged through pinned memory: no host synchronisation on this path
     SICP_CUDA(cudaMallocAsync(&d_pose, 56, st));
-    SICP_CUDA(cudaMemcpyAsync(d_pose, pose7, 56, cudaMemcpyHostToDevice, st));
+    PinnedBlock pb;
+    void* stage = pinned_stage(56, st, &pb);
+    if (!stage) { set_error("pinned staging allocation failed"); return SICP_ERR_CUDA; }
+    std::memcpy(stage, pose7, 56);
+    SICP_CUDA(cudaMemcpyAsync(d_pose, stage, 56, cudaMemcpyHostToDevice, st));
+    pinned_release(pb, st);
   }
   int* d_corr; float* d_d2;
   SICP_CUDA(cudaMallocAsync(&d_corr, sizeof(int) * k * std::max(1, q->nslots), st));
@@ -505,7 +510,7 @@ sicp_status sicp_knn_cloud(const sicp_cloud* tgt, const sicp_cloud* q, const dou
   if (q->nslots) unsort_knn_kernel<<<(q->nslots + 255) / 256, 256, 0, st>>>(q->view(), tgt->view(), k, d_corr, d_d2, d_idx_out, d_d2_out);
   SICP_CUDA(cudaGetLastError());
   SICP_CUDA(cudaFreeAsync(d_corr, st)); SICP_CUDA(cudaFreeAsync(d_d2, st));
-  if (d_pose) { SICP_CUDA(cudaStreamSynchronize(st)); SICP_CUDA(cudaFreeAsync(d_pose, st)); }
+  if (d_pose) SICP_CUDA(cudaFreeAsync(d_pose, st));
   if (d_map) SICP_CUDA(cudaFreeAsync(d_map, st));
   return SICP_OK;
 }

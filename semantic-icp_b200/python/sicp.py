@@ -195,6 +195,13 @@ def knn(target: Cloud, queries, k, pose7=None, q_labels=None):
     return idx, d2
 
 
+def knn_cloud(target: Cloud, queries: Cloud, k, d_idx_ptr, d_d2_ptr, pose7=None):
+    """Device-resident kNN (sicp_knn_cloud): queries are the points of `queries`; outputs go to the device buffers
+    d_idx_ptr (int32 [nq*k]) / d_d2_ptr (float32 [nq*k]) in the queries' original order.  Asynchronous on the current stream."""
+    p = np.ascontiguousarray(pose7, dtype=np.float64) if pose7 is not None else None
+    _check(lib().sicp_knn_cloud(target.h, queries.h, _p(p), C.c_int(k), C.c_void_p(d_idx_ptr), C.c_void_p(d_d2_ptr)))
+
+
 def correspondences(algo, src: Cloud, tgt: Cloud, opts: Options, pose7):
     kc = 4 if algo == ALGO_EM else 1
     idx = np.full((src.n, kc), -1, dtype=np.int32)

@@ -17,13 +17,13 @@ stats()
 nw = (n + 31) // 32
 src.precompute(20, 1e-3, p["cm"])
 s = stats()
-print("self kNN k=20: per warp: node expansions %.1f leaf scans %.1f phase2 iters %.1f ; per query insertions %.1f" % (s[0] / nw, s[1] / nw, s[3] / nw, s[2] / n))
+print("self kNN k=20: per warp: node expansions %.1f leaf scans %.1f phase2 iters %.1f ; per query insertions %.1f; lanes needing a scanned leaf %.1f, scans with <=8 needers %.0f%%, <=16 %.0f%%" % (s[0] / nw, s[1] / nw, s[3] / nw, s[2] / n, s[4] / max(1, s[1]), 100 * s[5] / max(1, s[1]), 100 * s[6] / max(1, s[1])))
 tgt.precompute(20, 1e-3, p["cm"]); stats()
 for k in (1, 4):
     for pose, name in ((p["init"], "identity"), (p["T_gt"], "T_gt")):
         sicp.knn(tgt, p["src_xyz"], k, pose7=pose)
         s = stats()
-        print("cross kNN k=%d at %s: per warp: node expansions %.1f leaf scans %.1f phase2 iters %.1f ; per query insertions %.1f" % (k, name, s[0] / nw, s[1] / nw, s[3] / nw, s[2] / n))
+        print("cross kNN k=%d at %s: per warp: node expansions %.1f leaf scans %.1f phase2 iters %.1f ; per query insertions %.1f; lanes needing a scanned leaf %.1f, scans with <=8 needers %.0f%%, <=16 %.0f%%" % (k, name, s[0] / nw, s[1] / nw, s[3] / nw, s[2] / n, s[4] / max(1, s[1]), 100 * s[5] / max(1, s[1]), 100 * s[6] / max(1, s[1])))
 opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
 r = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
 cyc = r["lm_cycles"]; ev = r["lm_evals_total"]
