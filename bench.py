@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=4, help="scan pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=8, help="scan pairs per step per GPU")
     ap.add_argument("--points", type=int, default=120_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -94,6 +94,8 @@ def measured_peak():
 def cpu_oracle_run(pair, threads=0):
     from oracle import oracle as O
 
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1; the baseline must not inherit that)
+    threads = threads or len(os.sched_getaffinity(0))
     r = O.align_em(pair["src_xyz"], pair["src_labels"], pair["tgt_xyz"], pair["tgt_labels"], pair["cm"], pair["init"], threads=threads)
     return r, (threads or O.num_threads())
 

@@ -57,7 +57,7 @@ typedef struct sicp_options {
   int min_class_points;     /* SEMANTIC only: class used iff source class size > this, 400    semantic_icp.hpp:51  */
   int max_lm_iterations;    /* 400                                  gicp.hpp:143                                   */
   int profile;              /* 1: record CUDA events per stage into sicp_result.stage_ms                            */
-  int max_concurrent;       /* sicp_register_batch: registrations in flight on one GPU (0 = default 4)              */
+  int max_concurrent;       /* sicp_register_batch: registrations in flight on one GPU (0 = default 8)              */
   int reserved[6];
 } sicp_options;
 

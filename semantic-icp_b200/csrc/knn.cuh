@@ -53,6 +53,7 @@ __device__ __forceinline__ uint32_t morton30(float x, float y, float z, const in
 #ifdef SICP_STATS
 static __device__ unsigned long long g_stats[8];  // per warp: 0 node expansions, 1 leaf scans, 3 phase-2 iterations; per lane: 2 insertions
 #define SICP_STAT(i, v) do { if ((threadIdx.x & 31) == 0 || (i) == 2) atomicAdd(&sicp::g_stats[i], (unsigned long long)(v)); } while (0)
+static __device__ unsigned g_warp_scans[16384], g_warp_cycles[16384];  // per query warp of the LAST search kernel: leaf scans, SM cycles
 #else
 #define SICP_STAT(i, v) do { } while (0)
 #endif
@@ -135,6 +136,11 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
   const int home = valid ? home_leaf(tv, sg, qx, qy, qz) : -1;
   int myseed = -1;   // lane i remembers the i-th seed leaf
   bool seeded = false;
+#ifdef SICP_STATS
+  unsigned dbg_scans = 0;
+  const long long dbg_t0 = clock64();
+  const int dbg_w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#endif
   // virtual root: expand the top level (<= kArity nodes); afterwards pop / expand / scan
   int level = top + 1, idx = 0;
   for (;;) {
@@ -209,6 +215,7 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       }
       SICP_STAT(1, 1);
 #ifdef SICP_STATS
+      dbg_scans++;
       { const unsigned mx = __reduce_max_sync(kFull, (unsigned)__popc(pass)); SICP_STAT(3, mx); }
 #endif
       while (pass) {
@@ -244,6 +251,9 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
     }
     if (!found) break;
   }
+#ifdef SICP_STATS
+  if (lane == 0 && dbg_w < 16384) { g_warp_scans[dbg_w] = dbg_scans; g_warp_cycles[dbg_w] = (unsigned)(clock64() - dbg_t0); }
+#endif
 }
 
 }  // namespace sicp

@@ -356,6 +356,18 @@ sicp_status sicp_debug_stats(unsigned long long* out8, int reset) {
   return SICP_OK;
 }
 
+// per-warp traversal trace of the last search kernel (stats build only): out[0..n) scans, out[n..2n) cycles
+sicp_status sicp_debug_warp_trace(unsigned* out, int n) {
+#ifdef SICP_STATS
+  SICP_CUDA(cudaDeviceSynchronize());
+  SICP_CUDA(cudaMemcpyFromSymbol(out, g_warp_scans, sizeof(unsigned) * n));
+  SICP_CUDA(cudaMemcpyFromSymbol(out + n, g_warp_cycles, sizeof(unsigned) * n));
+#else
+  for (int i = 0; i < 2 * n; i++) out[i] = 0;
+#endif
+  return SICP_OK;
+}
+
 sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, const double* cm) {
   SICP_REQUIRE(c, "cloud is null");
   SICP_REQUIRE(k_cov >= 1 && k_cov <= kMaxK, "k_cov must be in 1..32");

@@ -3,6 +3,7 @@
 // Replaces the bodies of GICP::align (impl/gicp.hpp:29-175), SemanticIterativeClosestPoint::align
 // (impl/semantic_icp.hpp:27-166) and EmIterativeClosestPoint::align (impl/em_icp.hpp:24-200).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -197,7 +198,11 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   }
   sicp_status rc = SICP_OK;
   const int kChunk = 3;
-  const int lm_grid = lm_grid_blocks(jobs[0].src->device) / (S > 1 ? 2 : 1);  // concurrent solves share every SM
+  // A lone solve takes every SM (2 CTAs each).  Concurrent solves get a quarter of that each: their sweeps are longer,
+  // so the latency-bound control step between sweeps idles a smaller share of the registers they hold, and kNN kernels
+  // of other registrations fit beside them.
+  int lm_grid = lm_grid_blocks(jobs[0].src->device) / (S > 1 ? 4 : 1);
+  if (const char* e = getenv("SICP_LM_GRID")) { const int g = atoi(e); if (g > 0 && S > 1) lm_grid = std::min(g, lm_grid_blocks(jobs[0].src->device)); }
   std::vector<int> slot_job(S, -1);
   int next = 0, live = 0;
   auto launch = [&](int slot) -> sicp_status {
@@ -292,7 +297,7 @@ sicp_status sicp_register_batch(int algo, size_t n_pairs, sicp_cloud* const* src
   std::memset(out, 0, sizeof(sicp_result) * n_pairs);
   std::vector<Job> jobs(n_pairs);
   for (size_t i = 0; i < n_pairs; i++) { jobs[i].algo = algo; jobs[i].src = src[i]; jobs[i].tgt = tgt[i]; jobs[i].opts = opts; jobs[i].out = out + i; }
-  return run_jobs(jobs, init7s, opts->max_concurrent > 0 ? opts->max_concurrent : 4);
+  return run_jobs(jobs, init7s, opts->max_concurrent > 0 ? opts->max_concurrent : 8);
 }
 
 sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* pose7, int32_t* idx_out,

@@ -28,3 +28,24 @@ opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
 r = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
 cyc = r["lm_cycles"]; ev = r["lm_evals_total"]
 print("LM: evals %d, cycles/eval: sweep %.0f wait %.0f control %.0f (reduce %.0f, state load %.0f, lm step %.0f)" % (ev, cyc[0] / ev, cyc[1] / ev, cyc[2] / ev, cyc[3] / ev, cyc[4] / ev, cyc[5] / ev))
+
+# per-warp cost distribution of one search kernel (load balance)
+def trace(nwarps):
+    buf = (C.c_uint * (2 * nwarps))()
+    L.sicp_debug_warp_trace(buf, C.c_int(nwarps))
+    a = np.array(buf[:], dtype=np.int64)
+    return a[:nwarps], a[nwarps:]
+def describe(name, sc, cy):
+    q = lambda a, p: np.percentile(a, p)
+    print("%s: scans/warp mean %.1f p50 %.0f p90 %.0f p99 %.0f max %d | cycles/warp mean %.0f p50 %.0f p90 %.0f p99 %.0f max %d (sum/max = %.0f warps' worth)" %
+          (name, sc.mean(), q(sc, 50), q(sc, 90), q(sc, 99), sc.max(), cy.mean(), q(cy, 50), q(cy, 90), q(cy, 99), cy.max(), cy.sum() / cy.max()))
+sicp.knn(tgt, p["src_xyz"], 4, pose7=p["T_gt"])
+sc, cy = trace(nw)
+describe("cross k=4", sc, cy)
+heavy = np.argsort(-cy)[:10]
+print("  heaviest warps:", [(int(i), int(sc[i]), int(cy[i])) for i in heavy])
+c2 = sicp.Cloud(p["src_xyz"], p["src_labels"]); c2.precompute(20, 1e-3, p["cm"])
+sc, cy = trace(nw)
+describe("self k=20", sc, cy)
+heavy = np.argsort(-cy)[:10]
+print("  heaviest warps:", [(int(i), int(sc[i]), int(cy[i])) for i in heavy])
