@@ -3,9 +3,12 @@
 // Replaces the bodies of GICP::align (impl/gicp.hpp:29-175), SemanticIterativeClosestPoint::align
 // (impl/semantic_icp.hpp:27-166) and EmIterativeClosestPoint::align (impl/em_icp.hpp:24-200).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 #include "kernels.h"
@@ -103,11 +106,19 @@ struct StageTimer {
   std::vector<int> stage;
   void begin(int s, cudaStream_t st) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); stage.push_back(s); }
   void end(cudaStream_t st) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); }
-  void collect(sicp_result* out) {
+  void collect(sicp_result* out, cudaEvent_t ref = nullptr, int job = 0) {
+    FILE* tf = nullptr;  // SICP_TRACE=<file>: append "job stage start_ms end_ms" (relative to the batch start) per timed launch
+    if (ref) { if (const char* path = getenv("SICP_TRACE")) tf = fopen(path, "a"); }
     for (size_t i = 0; i + 1 < ev.size(); i += 2) {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) { out->stage_ms[stage[i / 2]] += ms; out->stage_launches[stage[i / 2]]++; }
+      if (tf) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, ref, ev[i]); cudaEventElapsedTime(&t1, ref, ev[i + 1]);
+        fprintf(tf, "%d %d %.4f %.4f\n", job, stage[i / 2], t0, t1);
+      }
     }
+    if (tf) fclose(tf);
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     ev.clear(); stage.clear();
   }
@@ -128,18 +139,24 @@ struct Job {
     SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
     return SICP_OK;
   }
+  static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  double host_ms[4] = {0, 0, 0, 0};  // host time inside the launch calls of this job (kNN, E-step, LM, readback): diagnostics
   sicp_status enqueue_pass() {
     cudaStream_t st = ws.st;
     const int* stop = &ws.d_ctl->converged;
+    double h0 = now_ms();
     tm.begin(SICP_STAGE_KNN, st);
     SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, stop, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
     tm.end(st);
+    host_ms[0] += now_ms() - h0; h0 = now_ms();
     tm.begin(SICP_STAGE_ESTEP, st);
     SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, stop, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, ws.d_ctl, st));
     tm.end(st);
+    host_ms[1] += now_ms() - h0; h0 = now_ms();
     tm.begin(SICP_STAGE_LM, st);
     SICP_CHECK(launch_lm(src, cfg, ws.d_w, ws.d_gpt, ws.d_gnt, ws.d_ctl, ws.d_partials, ws.grid, st));
     tm.end(st);
+    host_ms[2] += now_ms() - h0;
     launches += 3;
     enqueued++;
     return SICP_OK;
@@ -154,6 +171,7 @@ struct Job {
   }
   // after the stream is synchronised: true when the registration is complete
   bool done_after_sync() const { return ws.h_ctl->converged != 0 || enqueued >= cfg.outer_cap + 2; }
+  cudaEvent_t trace_ref = nullptr; int trace_id = 0;
   void finish() {
     const RegCtl& c = *ws.h_ctl;
     std::memcpy(out->pose7, c.pose, 56);
@@ -166,7 +184,7 @@ struct Job {
     for (int i = 0; i < 3; i++) out->lm_cycles[i] = (double)c.dbg_cycles[i];
     for (int i = 0; i < 3; i++) out->lm_cycles[3 + i] = (double)c.dbg_cycles[4 + i];
     out->gpu_launches = c.outer * 3;  // kernels that did work (passes enqueued past convergence return immediately)
-    tm.collect(out);
+    tm.collect(out, trace_ref, trace_id);
     ws.release();
     finished = true;
   }
@@ -189,7 +207,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
       SICP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
       t_streams.push_back(s);
     }
-    SICP_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    SICP_CUDA(cudaEventCreate(&fork));
     SICP_CUDA(cudaEventRecord(fork, base));
     for (int s = 0; s < S; s++) {
       streams[s] = t_streams[s];
@@ -211,9 +229,13 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     Job& jb = jobs[j];
     cudaStream_t st = streams[slot];
     // covariances / label vectors on this job's stream (no-op when cached); other jobs sharing a cloud wait on its event
+    jb.tm.on = jb.opts->profile != 0;
+    jb.trace_ref = fork; jb.trace_id = j;
+    jb.tm.begin(SICP_STAGE_COV, st);
     sicp_set_stream(st);
     sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts);
     sicp_set_stream(base);
+    jb.tm.end(st);
     SICP_CHECK(r);
     if (jb.src->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.src->ready_ev, 0));
     if (jb.tgt->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.tgt->ready_ev, 0));
@@ -222,19 +244,43 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     live++;
     return SICP_OK;
   };
-  for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch(s);
+  // one completion event per slot, recorded after the control-block readback of each chunk.  The host POLLS the slots
+  // (cudaEventQuery) and serves whichever registration finished its chunk first; blocking on one stream would leave
+  // the streams of registrations that are already waiting for their next chunk empty.
+  std::vector<cudaEvent_t> ev(S, nullptr);
+  for (int s = 0; s < S; s++) SICP_CUDA(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
+  auto launch_and_mark = [&](int slot) -> sicp_status {
+    SICP_CHECK(launch(slot));
+    SICP_CUDA(cudaEventRecord(ev[slot], streams[slot]));
+    return SICP_OK;
+  };
+  for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch_and_mark(s);
   while (live > 0 && rc == SICP_OK) {
+    bool served = false;
     for (int s = 0; s < S && rc == SICP_OK; s++) {
       const int j = slot_job[s];
       if (j < 0) continue;
-      if (cudaStreamSynchronize(streams[s]) != cudaSuccess) { set_error(std::string("stream sync failed: ") + cudaGetErrorString(cudaGetLastError())); rc = SICP_ERR_CUDA; break; }
+      const cudaError_t q = S == 1 ? cudaEventSynchronize(ev[s]) : cudaEventQuery(ev[s]);
+      if (q == cudaErrorNotReady) continue;
+      if (q != cudaSuccess) { set_error(std::string("stream failed: ") + cudaGetErrorString(q)); rc = SICP_ERR_CUDA; break; }
+      served = true;
       if (jobs[j].done_after_sync()) {
         jobs[j].finish();
         live--;
         slot_job[s] = -1;
-        if (next < nj) rc = launch(s);
-      } else rc = jobs[j].enqueue_chunk(kChunk);
+        if (next < nj) rc = launch_and_mark(s);
+      } else {
+        rc = jobs[j].enqueue_chunk(kChunk);
+        if (rc == SICP_OK && cudaEventRecord(ev[s], streams[s]) != cudaSuccess) { set_error("event record failed"); rc = SICP_ERR_CUDA; }
+      }
     }
+    if (!served && rc == SICP_OK) std::this_thread::yield();
+  }
+  for (int s = 0; s < S; s++) if (ev[s]) cudaEventDestroy(ev[s]);
+  if (getenv("SICP_TRACE")) {
+    double h[3] = {0, 0, 0};
+    for (Job& jb : jobs) for (int i = 0; i < 3; i++) h[i] += jb.host_ms[i];
+    fprintf(stderr, "[sicp] host ms inside launches: kNN %.2f E-step %.2f LM %.2f (all jobs)\n", h[0], h[1], h[2]);
   }
   for (Job& jb : jobs) if (!jb.finished && jb.ws.st) jb.ws.release();
   if (S > 1) {
