@@ -21,6 +21,8 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxSeed = 24;                           // seed leaves injected before the traversal (see knn_search)
 constexpr int kStackCap = 8 * kMaxLevels + kMaxSeed;   // DFS over an 8-ary tree: <= 7 pending siblings per level, plus the seeds
 constexpr int kForced = 1 << 25;                       // stack entry flag: seed leaf (nleaf < 2^25)
+constexpr float kPrune = 1.0f - 1.0f / 262144.0f;      // packet-level bounds are deflated by 2^-18 before pruning: far above
+                                                       // the ~2^-21 relative rounding of a box gap or a point distance
 
 // ---- Morton quantisation shared by the build (cloud.cu) and the query-side home-leaf lookup
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -141,6 +143,17 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
   const long long dbg_t0 = clock64();
   const int dbg_w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 #endif
+  // AABB of the packet's (valid) queries, for the node tests of the expansion step
+  float pk_lo[3], pk_hi[3];
+  {
+    const float q[3] = {qx, qy, qz};
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      pk_lo[c] = ord2f(__reduce_min_sync(kFull, valid ? f2ord(q[c]) : 0x7fffffff));
+      pk_hi[c] = ord2f(__reduce_max_sync(kFull, valid ? f2ord(q[c]) : (int)0x80000000));
+    }
+  }
+  if (!__any_sync(kFull, valid)) return;
   // virtual root: expand the top level (<= kArity nodes); afterwards pop / expand / scan
   int level = top + 1, idx = 0;
   for (;;) {
@@ -149,18 +162,32 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       const int cl = level - 1;
       const int c0 = idx * kArity;
       const int nc = min(kArity, sg.node_cnt[cl] - c0);
+      // Stage 1, one lane per child: box-to-box lower bound between the child's AABB and the AABB of the packet's
+      // queries against the loosest k-th bound of the packet — conservative for every lane (kPrune covers the rounding
+      // of both sides).  Stage 2, only for the children that survive: the exact per-lane bound, whose minimum over the
+      // lanes that need the child is the ordering / culling key.
       unsigned mykey = 0x7f800000u;  // +inf: "not needed"
-      int mychild = 0;
-#pragma unroll
-      for (int j = 0; j < kArity; j++) {
-        if (j < nc) {
-          const int ni = sg.node_off[cl] + c0 + j;
-          const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
-          const float lb = box_lb_rn(qx, qy, qz, lo, hi);
-          const bool need = valid && !(lb > L.worst());
-          const unsigned kmin = __reduce_min_sync(kFull, need ? __float_as_uint(lb) : 0x7f800000u);  // lb >= 0: bit order == value order
-          if (lane == j) { mykey = kmin; mychild = c0 + j; }
-        }
+      const int mychild = c0 + lane;
+      const float wmax_e = __uint_as_float(__reduce_max_sync(kFull, valid ? __float_as_uint(L.worst()) : 0u));
+      bool maybe = false;
+      if (lane < nc) {
+        const int ni = sg.node_off[cl] + c0 + lane;
+        const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
+        const float gx = fmaxf(fmaxf(lo.x - pk_hi[0], pk_lo[0] - hi.x), 0.f);
+        const float gy = fmaxf(fmaxf(lo.y - pk_hi[1], pk_lo[1] - hi.y), 0.f);
+        const float gz = fmaxf(fmaxf(lo.z - pk_hi[2], pk_lo[2] - hi.z), 0.f);
+        maybe = !((gx * gx + gy * gy + gz * gz) * kPrune > wmax_e);
+      }
+      unsigned cand = __ballot_sync(kFull, maybe);
+      while (cand) {
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int ni = sg.node_off[cl] + c0 + j;
+        const float4 lo = __ldg(&tv.node_lo[ni]), hi = __ldg(&tv.node_hi[ni]);
+        const float lb = box_lb_rn(qx, qy, qz, lo, hi);
+        const bool need = valid && !(lb > L.worst());
+        const unsigned kmin = __reduce_min_sync(kFull, need ? __float_as_uint(lb) : 0x7f800000u);  // lb >= 0: bit order == value order
+        if (lane == j) mykey = kmin;
       }
       // rank of child `lane` among the 8 (ties by child index); needed children have the smallest ranks
       int rank = 0;
