@@ -55,27 +55,6 @@ __device__ __forceinline__ double det_S(const double* u, const double* v, double
   return 2.0 * (a - be) * (a + be);
 }
 
-// Ceres loss compositions: rho(s) and rho'(s) at s = r^2.
-__device__ __forceinline__ void loss_eval(int algo, double w, double s, double* rho0, double* rho1) {
-  if (algo == SICP_ALGO_SEMANTIC) {  // CauchyLoss(1.5)
-    const double b = 2.25, c = 1.0 / 2.25;
-    const double sum = 1.0 + s * c, inv = 1.0 / sum;
-    *rho0 = b * log(sum);
-    *rho1 = fmax(DBL_MIN, inv);
-    return;
-  }
-  // ComposedLoss(CauchyLoss(3.0) [scaled by w for EM], SQLoss)
-  const double v = s + DBL_EPSILON;
-  const double g0 = sqrt(v);
-  const double g1 = 1.0 / (2.0 * g0);
-  const double b = 9.0, c = 1.0 / 9.0;
-  const double sum = 1.0 + g0 * c, inv = 1.0 / sum;
-  double f0 = b * log(sum), f1 = fmax(DBL_MIN, inv);
-  if (algo == SICP_ALGO_EM) { f0 *= w; f1 *= w; }
-  *rho0 = f0;
-  *rho1 = f1 * g1;
-}
-
 // ------------------------------------------------------------------ K3: E-step
 // One thread per candidate pair (slot, c).  Besides the weight it GATHERS the target point and normal of the pair
 // into residual-ordered arrays, so that the many LM sweeps of the pass stream them with coalesced loads instead of
@@ -149,6 +128,7 @@ struct LMState {
   double scale[6], diag[6];
   double radius, decrease_factor, x_norm, gmax, model;
   int reuse_diag, last_successful, invalid, iter, evals, term, done, started;
+  int pad0, pad1;
 };
 struct LMSync {
   unsigned count;              // blocks that finished the current sweep
@@ -160,42 +140,6 @@ enum { TERM_NO_CONV = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 
 
 __device__ __forceinline__ int tri(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
 
-// (Hs + diag/radius) y = gs by Cholesky, fully unrolled (registers), reciprocal pivots
-__device__ __forceinline__ bool chol_solve6(const double* Hs, const double* dg, double inv_radius, const double* b, double* x) {
-  double L[21], inv[6];
-  bool ok = true;
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-#pragma unroll
-    for (int j = 0; j <= i; j++) {
-      double s = Hs[6 * i + j] + (i == j ? dg[i] * inv_radius : 0.0);
-#pragma unroll
-      for (int k = 0; k < j; k++) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-      if (i == j) {
-        ok = ok && (s > 0);
-        inv[i] = rsqrt(s);  // the pivot itself is never needed: only its reciprocal
-      } else {
-        L[i * (i + 1) / 2 + j] = s * inv[j];
-      }
-    }
-  }
-  double y[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    double s = b[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) s -= L[i * (i + 1) / 2 + k] * y[k];
-    y[i] = s * inv[i];
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; i--) {
-    double s = y[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; k++) s -= L[k * (k + 1) / 2 + i] * x[k];
-    x[i] = s * inv[i];
-  }
-  return ok;
-}
 // T * exp(delta) (local_parameterization_se3.h:22) on the LM critical path: one sincos, reciprocal multiplies and an
 // rsqrt renormalisation instead of the divisions / square roots of the general-purpose se3.cuh routines.
 __device__ __forceinline__ void pose_plus_fast(const double* x7, const double* d, double* out7) {
@@ -265,94 +209,161 @@ __device__ __forceinline__ double norm7(const double* a) {
   for (int i = 0; i < 7; i++) s += a[i] * a[i];
   return sqrt(s);
 }
-// adopt the evaluation in `tot` as the current linearisation point
-__device__ __forceinline__ void lm_adopt(LMState& S, const double* tot, bool first) {
+// Warp-cooperative form of lm_control (same decisions, same state), run by warp 0 of the controller block.
+// The single-thread version is bound by latency: ~500 dependent FP64 ops at 8 cycles plus a 29-cycle shared-memory
+// round trip for every access to the solver state.  Here every lane loads the scalar state into registers ONCE, all
+// lanes make the (uniform) decisions redundantly, and the 6x6 work is spread over lanes: lane i owns row i of the
+// scaled Gauss-Newton system (formed in registers), of the Cholesky factor and of the triangular solves (pivots and
+// solution components travel by shuffle); the model decrease is a 6-lane dot product.  State goes back to shared
+// memory once, at the end.
+__device__ __forceinline__ void lm_control_warp(LMState& S, const double* tot, int max_iter, double* s_L, int lane) {
+  const double ftol = 0.1 * kSophusEps, gtol = 0.1 * kSophusEps, ptol = 1e-8;
+  const int i = lane < 6 ? lane : 0;  // lanes >= 6 shadow row 0; nothing is ever read from them
+  // ---- state -> registers
+  double x[7], cand[7], scale[6], Hrow[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) S.g[i] = tot[21 + i];
-  S.cost = tot[27];
-  if (first)
+  for (int q = 0; q < 7; q++) { x[q] = S.x[q]; cand[q] = S.cand[q]; }
 #pragma unroll
-    for (int j = 0; j < 6; j++) S.scale[j] = 1.0 / (1.0 + sqrt(tot[tri(j, j)]));  // Jacobi scaling, computed once
+  for (int j = 0; j < 6; j++) { scale[j] = S.scale[j]; Hrow[j] = S.Hs[6 * i + j]; }
+  double gs_i = S.gs[i], diag_i = S.diag[i];
+  double radius = S.radius, decrease = S.decrease_factor, x_norm = S.x_norm, gmax = S.gmax, model = S.model, cost = S.cost;
+  int reuse_diag = S.reuse_diag, last_successful = S.last_successful, invalid = S.invalid, iter = S.iter, term = S.term, done = 0;
+  const int started = S.started;
+  // ---- iteration zero, or accept / reject the evaluated candidate (uniform)
+  int adopt = 0;
+  if (!started) {
+    radius = 1e4; decrease = 2.0; reuse_diag = 0; last_successful = 1; invalid = 0; iter = 0; term = TERM_NO_CONV;
+    adopt = 1;
+  } else {
+    const double cost_change = cost - tot[27];
+    if (fabs(cost_change) <= ftol * cost) { term = TERM_FUNCTION; done = 1; }  // candidate not applied
+    else {
+      const double rel = cost_change / model;
+      if (rel > 1e-3) {
 #pragma unroll
-  for (int a = 0; a < 6; a++) {
-    S.gs[a] = S.g[a] * S.scale[a];
-#pragma unroll
-    for (int b = 0; b < 6; b++) S.Hs[6 * a + b] = tot[tri(a, b)] * S.scale[a] * S.scale[b];
-  }
-  S.gmax = grad_max_norm(S.x, S.g);
-  S.x_norm = norm7(S.x);
-}
-// top of the minimizer loop up to the candidate point; sets S.done when the solve terminates
-__device__ __forceinline__ void lm_propose(LMState& S, int max_iter) {
-  const double gtol = 0.1 * kSophusEps, ptol = 1e-8;
-  for (;;) {
-    if (S.iter >= max_iter) { S.term = TERM_NO_CONV; S.done = 1; return; }
-    if (S.last_successful && S.gmax <= gtol) { S.term = TERM_GRADIENT; S.done = 1; return; }
-    if (S.radius <= 1e-32) { S.term = TERM_RADIUS; S.done = 1; return; }
-    S.iter++;
-    if (!S.reuse_diag)
-#pragma unroll
-      for (int j = 0; j < 6; j++) S.diag[j] = fmin(fmax(S.Hs[7 * j], 1e-6), 1e32);
-    double y[6];
-    const bool ok = chol_solve6(S.Hs, S.diag, 1.0 / S.radius, S.gs, y);
-    S.reuse_diag = 1;
-    double model = 0;
-    if (ok) {
-      double sg = 0, sHs = 0;
-#pragma unroll
-      for (int a = 0; a < 6; a++) {
-        double row = 0;
-#pragma unroll
-        for (int b = 0; b < 6; b++) row += S.Hs[6 * a + b] * y[b];
-        sg += y[a] * S.gs[a];
-        sHs += y[a] * row;
+        for (int q = 0; q < 7; q++) x[q] = cand[q];
+        const double t = 2.0 * rel - 1.0;
+        radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+        decrease = 2.0; reuse_diag = 0; last_successful = 1;
+        adopt = 2;
+      } else {
+        radius = radius / decrease; decrease *= 2.0; reuse_diag = 1; last_successful = 0;
       }
-      model = sg - 0.5 * sHs;  // step = -y:  -step.gs - 1/2 step.Hs.step
     }
-    if (!ok || !(model > 0)) {
-      if (++S.invalid >= 5) { S.term = TERM_FAIL; S.done = 1; return; }
-      S.radius /= S.decrease_factor; S.decrease_factor *= 2.0; S.last_successful = 0;
+  }
+  // ---- adopt the evaluation in `tot` as the linearisation point (lm_adopt)
+  if (adopt && !done) {
+    double g[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      g[j] = tot[21 + j];
+      if (adopt == 1) scale[j] = 1.0 / (1.0 + sqrt(tot[tri(j, j)]));  // Jacobi scaling, computed once
+    }
+    double scale_i = scale[0], g_i = g[0];
+#pragma unroll
+    for (int j = 1; j < 6; j++) { scale_i = (i == j) ? scale[j] : scale_i; g_i = (i == j) ? g[j] : g_i; }
+#pragma unroll
+    for (int j = 0; j < 6; j++) Hrow[j] = tot[tri(i, j)] * scale_i * scale[j];
+    gs_i = g_i * scale_i;
+    cost = tot[27];
+    gmax = grad_max_norm(x, g);
+    x_norm = norm7(x);
+    if (lane < 6) S.g[lane] = g_i;
+  }
+  // ---- propose the next candidate (lm_propose); repeats only after an invalid step
+  while (!done) {
+    if (iter >= max_iter) { term = TERM_NO_CONV; done = 1; break; }
+    if (last_successful && gmax <= gtol) { term = TERM_GRADIENT; done = 1; break; }
+    if (radius <= 1e-32) { term = TERM_RADIUS; done = 1; break; }
+    iter++;
+    if (!reuse_diag) {
+      double h = Hrow[0];
+#pragma unroll
+      for (int j = 1; j < 6; j++) h = (i == j) ? Hrow[j] : h;
+      diag_i = fmin(fmax(h, 1e-6), 1e32);
+    }
+    reuse_diag = 1;
+    // Cholesky of (Hs + diag/radius), row i in this lane
+    const double dmp = diag_i / radius;
+    double A[6], Lr[6], inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) A[j] = Hrow[j] + (i == j ? dmp : 0.0);
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      const double piv = __shfl_sync(kFullMask, A[j], j);
+      ok = ok && (piv > 0);
+      inv[j] = rsqrt(piv);
+      Lr[j] = A[j] * inv[j];
+#pragma unroll
+      for (int k = j + 1; k < 6; k++) A[k] -= Lr[j] * __shfl_sync(kFullMask, Lr[j], k);
+    }
+    // forward substitution L y = gs (every lane ends up with all of y)
+    double r = gs_i, y[6];
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      y[j] = __shfl_sync(kFullMask, r, j) * inv[j];
+      r -= Lr[j] * y[j];
+    }
+    // back substitution L^T s = y needs columns of L: through shared memory
+    __syncwarp();
+    if (lane < 6)
+#pragma unroll
+      for (int j = 0; j < 6; j++) s_L[6 * lane + j] = Lr[j];
+    __syncwarp();
+    double sv = y[0];
+#pragma unroll
+    for (int j = 1; j < 6; j++) sv = (i == j) ? y[j] : sv;
+    double sol[6];
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+      sol[k] = __shfl_sync(kFullMask, sv, k) * inv[k];
+      sv -= s_L[6 * k + i] * sol[k];
+    }
+    // model decrease  sol.gs - sol.Hs.sol / 2  (step = -sol)
+    double row = 0, si = sol[0];
+#pragma unroll
+    for (int j = 0; j < 6; j++) { row += Hrow[j] * sol[j]; si = (i == j) ? sol[j] : si; }
+    double tsum = lane < 6 ? si * (gs_i - 0.5 * row) : 0.0;
+    tsum += __shfl_xor_sync(kFullMask, tsum, 1);
+    tsum += __shfl_xor_sync(kFullMask, tsum, 2);
+    tsum += __shfl_xor_sync(kFullMask, tsum, 4);
+    const double mdl = __shfl_sync(kFullMask, tsum, 0);
+    if (!ok || !(mdl > 0)) {
+      if (++invalid >= 5) { term = TERM_FAIL; done = 1; break; }
+      radius /= decrease; decrease *= 2.0; last_successful = 0;
       continue;
     }
-    S.invalid = 0;
-    S.model = model;
+    invalid = 0;
+    model = mdl;
     double delta[6];
 #pragma unroll
-    for (int j = 0; j < 6; j++) delta[j] = -y[j] * S.scale[j];
-    pose_plus_fast(S.x, delta, S.cand);
+    for (int j = 0; j < 6; j++) delta[j] = -sol[j] * scale[j];
+    pose_plus_fast(x, delta, cand);
     double sn = 0;
 #pragma unroll
-    for (int i = 0; i < 7; i++) sn += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
-    if (sqrt(sn) <= ptol * (S.x_norm + ptol)) { S.term = TERM_PARAMETER; S.done = 1; return; }  // candidate not applied
-    return;
+    for (int q = 0; q < 7; q++) sn += (x[q] - cand[q]) * (x[q] - cand[q]);
+    if (sqrt(sn) <= ptol * (x_norm + ptol)) { term = TERM_PARAMETER; done = 1; }  // candidate not applied
+    break;
   }
-}
-// One control step after a sweep whose totals are in `tot`: iteration zero, or accept/reject + next proposal.
-__device__ __noinline__ void lm_control(LMState& S, const double* tot, int max_iter) {
-  S.evals++;
-  if (!S.started) {
-    S.started = 1;
-    S.radius = 1e4; S.decrease_factor = 2.0; S.reuse_diag = 0; S.last_successful = 1; S.invalid = 0; S.iter = 0; S.term = TERM_NO_CONV;
-    lm_adopt(S, tot, true);
-    lm_propose(S, max_iter);
-    return;
-  }
-  const double ftol = 0.1 * kSophusEps;
-  const double cand_cost = tot[27];
-  const double cost_change = S.cost - cand_cost;
-  if (fabs(cost_change) <= ftol * S.cost) { S.term = TERM_FUNCTION; S.done = 1; return; }  // candidate not applied
-  const double rel = cost_change / S.model;
-  if (rel > 1e-3) {
+  // ---- registers -> state
+  if (lane < 6) {
 #pragma unroll
-    for (int i = 0; i < 7; i++) S.x[i] = S.cand[i];
-    lm_adopt(S, tot, false);
-    const double t = 2.0 * rel - 1.0;
-    S.radius = fmin(1e16, S.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
-    S.decrease_factor = 2.0; S.reuse_diag = 0; S.last_successful = 1;
-  } else {
-    S.radius = S.radius / S.decrease_factor; S.decrease_factor *= 2.0; S.reuse_diag = 1; S.last_successful = 0;
+    for (int j = 0; j < 6; j++) S.Hs[6 * lane + j] = Hrow[j];
+    S.gs[lane] = gs_i; S.diag[lane] = diag_i;
+    double sc = scale[0];
+#pragma unroll
+    for (int j = 1; j < 6; j++) sc = (lane == j) ? scale[j] : sc;
+    S.scale[lane] = sc;
   }
-  lm_propose(S, max_iter);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < 7; q++) { S.x[q] = x[q]; S.cand[q] = cand[q]; }
+    S.radius = radius; S.decrease_factor = decrease; S.x_norm = x_norm; S.gmax = gmax; S.model = model; S.cost = cost;
+    S.reuse_diag = reuse_diag; S.last_successful = last_successful; S.invalid = invalid; S.iter = iter; S.term = term; S.done = done;
+    S.started = 1; S.evals++;
+  }
+  __syncwarp();
 }
 
 struct LMArgs {
@@ -614,6 +625,7 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
   __shared__ double s_rot[kAcc];
   __shared__ double s_x[8];  // pose to evaluate [7] + done flag
   __shared__ double s_RT[12];  // its rotation matrix (row-major) and translation
+  __shared__ double s_L[36];   // Cholesky factor scratch of lm_control_warp
   LMSync* sy = a.sync;
   const bool eval_only = a.eval_pose != nullptr;
   const bool controller = blockIdx.x == 0;
@@ -636,12 +648,12 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
     sweep_acc<ALGO, KC>(a, s_RT, acc);
     block_reduce(acc, s_acc, a.partials);
     gen++;
-    __threadfence();
-    __syncthreads();
+    __syncthreads();  // the block's partial sums are written; thread 0's gpu-scope fence below is cumulative over them
     t_comp += clock64() - t0;
     t0 = clock64();
     if (!controller) {
       if (threadIdx.x == 0) {
+        __threadfence();
         atomicAdd(&sy->count, 1u);
         if (!eval_only) while ((int)(ld_acquire(&sy->flag) - gen) < 0) __nanosleep(32);
       }
@@ -665,13 +677,16 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
         if (threadIdx.x == 0) sy->count = 0;
         return;
       }
-      if (threadIdx.x == 0) {
-        if (!S.started) {
+      if (threadIdx.x < 32) {
+        if (threadIdx.x == 0 && !S.started) {
           double* ss = reinterpret_cast<double*>(&S);
           for (int i = 0; i < (int)(sizeof(LMState) / sizeof(double)); i++) ss[i] = 0.0;
           for (int i = 0; i < 7; i++) S.x[i] = s_x[i];
         }
-        lm_control(S, s_rot, a.cfg.max_iter);
+        __syncwarp();
+        lm_control_warp(S, s_rot, a.cfg.max_iter, s_L, threadIdx.x);
+      }
+      if (threadIdx.x == 0) {
         t_lm += clock64() - t1;
         if (S.done) {
           // outer-loop bookkeeping: mse = |log(cur^-1 est)|^2 (impl/gicp.hpp:153), stop rule, pass trace
@@ -701,8 +716,7 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
         s_x[7] = S.done ? 1.0 : 0.0;
         sy->bcast[7] = s_x[7];
         sy->count = 0;
-        __threadfence();
-        st_release(&sy->flag, gen);
+        st_release(&sy->flag, gen);  // release: the broadcast record and the counter reset above are visible before the flag
       }
       __syncthreads();
       t_ctl += clock64() - t0;

@@ -251,3 +251,64 @@ def test_errors(sicp, room):
     g = sicp.Cloud(room["src_xyz"])
     with pytest.raises(sicp.SicpError):
         g.normals()  # precompute has not run
+
+
+# ------------------------------------------------------------------------------------------------ degenerate inputs
+def test_degenerate_clouds_knn_and_covariances(sicp, oracle):
+    rng = np.random.default_rng(11)
+    cases = {
+        "identical": np.tile(np.array([[1.5, -2.0, 0.25]], dtype=np.float32), (300, 1)),       # zero-extent bounding box
+        "collinear": np.outer(np.linspace(0, 50, 400), [1, 2, -1]).astype(np.float32),          # rank-1 covariances
+        "coplanar_far": (np.c_[rng.uniform(-3, 3, (500, 2)), np.zeros(500)] + np.array([8000.0, -9000.0, 50.0])).astype(np.float32),  # f32 cancellation at 1e4 m
+        "lattice": np.stack(np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij"), -1).reshape(-1, 3).astype(np.float32),
+    }
+    for name, xyz in cases.items():
+        c = sicp.Cloud(xyz)
+        q = xyz[:: max(1, len(xyz) // 97)]
+        for k in (1, 4, 20):
+            idx, d2 = sicp.knn(c, q, k)
+            ridx, rd2 = oracle.knn(xyz, q, k, brute=True)
+            assert np.array_equal(idx, ridx), (name, k)
+            assert np.array_equal(d2, rd2), (name, k)
+        c.precompute(20, 1e-3)
+        ref = oracle.covariances(xyz, 20, 1e-3, want_nn=True)
+        assert np.array_equal(c.self_neighbours(), ref["nn"]), name
+        assert np.array_equal(c.normals(), ref["normals"]), name   # same Jacobi sweeps even on rank-deficient input
+
+
+def test_empty_problem_and_tiny_clouds(sicp, oracle, pkg):
+    rng = np.random.default_rng(0)
+    src = rng.normal(size=(50, 3)).astype(np.float32)
+    tgt = src + np.float32(1000.0)                                  # every correspondence fails the 250 m^2 gate
+    init = oracle.se3_exp([0.1, 0.2, 0.3, 0.01, 0.02, 0.03])
+    res = sicp.register(sicp.ALGO_GICP, sicp.Cloud(src), sicp.Cloud(tgt), sicp.default_options(sicp.ALGO_GICP), init)
+    ref = oracle.align_gicp(src, tgt, init)
+    assert np.array_equal(res["pose"], init) and np.array_equal(ref["pose"], init)   # empty problem leaves the pose unchanged
+    assert res["outer_iter"] == ref["outer_iter"] == 1 and res["n_corr_last"] == 0
+    # fewer target points than correspondences asked for (EM wants 4): the missing ones are reported as -1
+    tiny = sicp.Cloud(src[:3])
+    idx, d2 = sicp.knn(tiny, src[:10], 4)
+    assert np.all(idx[:, 3] == -1) and np.all(np.isinf(d2[:, 3])) and np.all(idx[:, :3] >= 0)
+    # zero-point cloud: creation and queries are legal, nothing is found
+    empty = sicp.Cloud(np.zeros((0, 3), dtype=np.float32))
+    idx, d2 = sicp.knn(empty, src[:5], 1)
+    assert np.all(idx == -1)
+
+
+def test_semantic_class_rules(sicp, oracle, pkg):
+    """semantic_icp.hpp:50-51: a class is used only if the target has it and the source class has > 400 points."""
+    p = pkg.synth.room_pair(seed=21, n_points=6000)
+    sl, tl = p["src_labels"].copy(), p["tgt_labels"].copy()
+    tl[tl == 3] = 4                     # class 3 absent from the target
+    small = np.nonzero(sl == 5)[0]
+    sl[small[350:]] = 6                 # class 5 shrinks to 350 source points (<= 400)
+    src = sicp.Cloud(p["src_xyz"], sl, layout=sicp.CLOUD_PER_CLASS)
+    tgt = sicp.Cloud(p["tgt_xyz"], tl, layout=sicp.CLOUD_PER_CLASS)
+    opts = sicp.default_options(sicp.ALGO_SEMANTIC)
+    idx, w, d2 = sicp.correspondences(sicp.ALGO_SEMANTIC, src, tgt, opts, p["init"])
+    ref = oracle.align_semantic(p["src_xyz"], sl, p["tgt_xyz"], tl, p["init"])
+    assert np.array_equal(idx, ref["corr0"])
+    assert np.all(idx[sl == 3] == -1) and np.all(idx[sl == 5] == -1)
+    res = sicp.register(sicp.ALGO_SEMANTIC, src, tgt, opts, p["init"])
+    rot, trans = pkg.synth.pose_error(res["pose"], ref["pose"])
+    assert rot < ROT_TOL and trans < TRANS_TOL and res["outer_iter"] == ref["outer_iter"]
