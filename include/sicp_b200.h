@@ -171,6 +171,23 @@ sicp_status sicp_fused_labels(sicp_cloud* src, sicp_cloud* tgt, const sicp_optio
  * out_xyz (host, out_stride bytes apart) = float math M4f * p for the cloud's points in original order. */
 sicp_status sicp_cloud_transform_f32(const sicp_cloud* cloud, const double* pose7, void* out_xyz, size_t out_stride);
 
+/* ---- evaluation steps either side of the path ----------------------------------------
+ * Label agreement (exec/roc_metrics.h:21-41, exec/nyu_metrics.h:36-84): for every source point (mapped by pose7 when
+ * it is not NULL; the reference passes the already transformed final cloud) the nearest target point; pairs with
+ * d2 < gate_d2 (25 in the reference) contribute (label_source, label_target).
+ *   confusion_out [n_labels*n_labels] counts, row = source label (may be NULL when n_labels == 0);
+ *   stats3_out    { label matches, gated pairs, sum of sqrt(d2) }  -> accuracy = [0]/[1], mean distance = [2]/[1];
+ *   pairs_out     [2*n_source] (label_source, label_target) in source order, 0xffffffff where gated out (nullable). */
+sicp_status sicp_label_agreement(const sicp_cloud* src, const sicp_cloud* tgt, const double* pose7, double gate_d2, int n_labels,
+                                 int64_t* confusion_out, double* stats3_out, uint32_t* pairs_out);
+/* SE(3) error of estimates against ground truth (exec/kitti_metrics.h:31-37): diff = GT * est^-1,
+ * err3s[3*i..] = { |log(diff)|^2, |log_SO3(diff)|^2, |translation(diff)|^2 }.  Host arithmetic (a few hundred flops per pose). */
+sicp_status sicp_pose_errors(size_t n, const double* gt7s, const double* est7s, double* err3s);
+/* Range filter of a raw scan (exec/filter_range.h:6-18, used at exec/kitti_eval.cc:124-127): indices (ascending) of the
+ * points with x*x+y*y+z*z <= range^2 (float products and sums like the reference), replacing its O(n^2) erase loop. */
+sicp_status sicp_filter_range(const void* xyz, size_t xyz_stride, size_t n, double range, int device, uint32_t* keep_idx_out,
+                              size_t* n_keep_out);
+
 #ifdef __cplusplus
 }
 #endif

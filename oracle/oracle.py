@@ -252,3 +252,41 @@ def label_split(labels):
     order = np.empty(n, dtype=np.int32)
     nc = lib().orc_label_split(_p(labels), C.c_int(n), _p(cl), _p(cs), _p(order))
     return cl[:nc].copy(), cs[: nc + 1].copy(), order
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Evaluation steps either side of the registration path, restated in numpy on top of the
+# oracle's exact kNN / SE(3) routines.
+
+
+def label_agreement(sxyz, slab, txyz, tlab, n_labels, gate=25.0, pose7=None):
+    """exec/roc_metrics.h:21-41 and exec/nyu_metrics.h:36-84: 1-NN of every source point in the target; pairs with
+    d2 < 25 give (label_source, label_target), the confusion counts, inlier / total counts and the summed distance."""
+    sxyz, txyz = _f32(sxyz), _f32(txyz)
+    q = transform_points(pose7, sxyz) if pose7 is not None else sxyz
+    idx, d2 = knn(txyz, q, 1)
+    slab, tlab = _u32(slab), _u32(tlab)
+    keep = (idx[:, 0] >= 0) & (d2[:, 0].astype(np.float64) < gate)                     # nyu_metrics.h:56
+    ls, lt = slab[keep], tlab[idx[keep, 0]]
+    conf = np.zeros((n_labels, n_labels), dtype=np.int64)
+    np.add.at(conf, (ls, lt), 1)                                                        # nyu_metrics.h:59
+    dist = 0.0
+    for v in np.sqrt(d2[keep, 0]):                                                      # float sqrt, sequential double sum (:64)
+        dist += float(v)
+    pairs = np.full((sxyz.shape[0], 2), 0xFFFFFFFF, dtype=np.uint32)
+    pairs[keep, 0], pairs[keep, 1] = ls, lt
+    return dict(confusion=conf, inliers=float(np.sum(ls == lt)), total=float(keep.sum()), dist=dist, pairs=pairs)
+
+
+def pose_errors(gt7, est7):
+    """exec/kitti_metrics.h:31-37: diff = GT * est^-1 -> (|log diff|^2, |log_SO3 diff|^2, |t diff|^2)."""
+    d = se3_mul(gt7, se3_inv(est7))
+    lg = se3_log(d)
+    return np.array([float(lg @ lg), float(lg[3:] @ lg[3:]), float(d[4:] @ d[4:])])
+
+
+def filter_range(xyz, rng):
+    """exec/filter_range.h:6-18: drop points with x*x+y*y+z*z (float arithmetic) > range*range (double)."""
+    xyz = _f32(xyz)
+    r2 = (xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2]
+    return np.nonzero(~(r2.astype(np.float64) > rng * rng))[0].astype(np.uint32)

@@ -52,7 +52,8 @@ EXPORTS = [
     "sicp_cloud_create_device", "sicp_cloud_destroy", "sicp_cloud_size", "sicp_cloud_precompute", "sicp_cloud_get_covariances",
     "sicp_cloud_get_normals", "sicp_cloud_get_label_distributions", "sicp_cloud_get_label_vectors", "sicp_cloud_get_self_neighbours",
     "sicp_cloud_get_classes", "sicp_knn", "sicp_knn_cloud", "sicp_correspondences", "sicp_evaluate", "sicp_register",
-    "sicp_register_batch", "sicp_fused_labels", "sicp_cloud_transform_f32", "sicp_launch_count",
+    "sicp_register_batch", "sicp_fused_labels", "sicp_cloud_transform_f32", "sicp_launch_count", "sicp_label_agreement",
+    "sicp_pose_errors", "sicp_filter_range",
 ]
 
 
@@ -243,6 +244,34 @@ def fused_labels(src: Cloud, tgt: Cloud, opts: Options, pose7):
     p = np.ascontiguousarray(pose7, dtype=np.float64)
     _check(lib().sicp_fused_labels(src.h, tgt.h, C.byref(opts), _p(p), _p(out)))
     return out
+
+
+def label_agreement(src: Cloud, tgt: Cloud, n_labels, gate_d2=25.0, pose7=None, want_pairs=False):
+    """exec/roc_metrics.h:21-41 / exec/nyu_metrics.h:36-84 on the device (sicp_label_agreement)."""
+    conf = np.zeros((n_labels, n_labels), dtype=np.int64)
+    stats = np.zeros(3)
+    pairs = np.empty((src.n, 2), dtype=np.uint32) if want_pairs else None
+    p = np.ascontiguousarray(pose7, dtype=np.float64) if pose7 is not None else None
+    _check(lib().sicp_label_agreement(src.h, tgt.h, _p(p), C.c_double(gate_d2), C.c_int(n_labels), _p(conf), _p(stats), _p(pairs)))
+    return dict(confusion=conf, inliers=stats[0], total=stats[1], dist=stats[2], pairs=pairs)
+
+
+def pose_errors(gt7s, est7s):
+    """exec/kitti_metrics.h:31-37 (sicp_pose_errors): rows of (|log diff|^2, |log_SO3 diff|^2, |t diff|^2)."""
+    g = np.ascontiguousarray(gt7s, dtype=np.float64).reshape(-1, 7)
+    e = np.ascontiguousarray(est7s, dtype=np.float64).reshape(-1, 7)
+    out = np.empty((g.shape[0], 3))
+    _check(lib().sicp_pose_errors(C.c_size_t(g.shape[0]), _p(g), _p(e), _p(out)))
+    return out
+
+
+def filter_range(xyz, rng, device=0):
+    """exec/filter_range.h:6-18 (sicp_filter_range): indices of the points within `rng` of the origin."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    keep = np.empty(xyz.shape[0], dtype=np.uint32)
+    n = C.c_size_t()
+    _check(lib().sicp_filter_range(_p(xyz), C.c_size_t(12), C.c_size_t(xyz.shape[0]), C.c_double(rng), C.c_int(device), _p(keep), C.byref(n)))
+    return keep[: n.value].copy()
 
 
 # ------------------------------------------------------------------------------------------------------------------

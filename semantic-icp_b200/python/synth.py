@@ -113,7 +113,7 @@ class Scene:
                 s = ((p0 - o) @ nrm) / denom
             ok = (np.abs(denom) > 1e-12) & (s > 1e-6) & (s < best)
             if bounds is not None:
-                hit = o + s[:, None] * dirs
+                hit = o + np.where(ok, s, 0.0)[:, None] * dirs  # rays parallel to the plane have s = inf/nan: they are not `ok`
                 lo, hi = bounds
                 ok &= np.all(hit >= lo - 1e-9, axis=1) & np.all(hit <= hi + 1e-9, axis=1)
             best = np.where(ok, s, best)
