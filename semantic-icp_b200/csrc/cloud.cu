@@ -10,6 +10,7 @@
 #include <unordered_map>
 #include "common.cuh"
 #include "knn.cuh"
+#include "se3.cuh"
 
 namespace sicp {
 
@@ -159,14 +160,18 @@ __global__ void upper_box_kernel(const Segment* __restrict__ seg, float4* node_l
     __syncthreads();
   }
 }
-__global__ void pack_xyz_kernel(const float4* __restrict__ pts, int nslots, float* xyz_out) {  // slots -> original order
+struct Mat34f { float m[12]; };  // rows of a float 4x4 (last row 0 0 0 1)
+// slots -> original order, p' = M * p in float arithmetic, left to right, no FMA contraction (x86 float code has none)
+__global__ void transform_f32_kernel(const float4* __restrict__ pts, int nslots, Mat34f M, float* __restrict__ xyz_out) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nslots) return;
-  float4 p = pts[s];
-  int o = __float_as_int(p.w);
-  if (o >= 0) { xyz_out[3 * (size_t)o] = p.x; xyz_out[3 * (size_t)o + 1] = p.y; xyz_out[3 * (size_t)o + 2] = p.z; }
+  const float4 p = pts[s];
+  const int o = __float_as_int(p.w);
+  if (o < 0) return;
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    xyz_out[3 * (size_t)o + r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M.m[4 * r], p.x), __fmul_rn(M.m[4 * r + 1], p.y)), __fmul_rn(M.m[4 * r + 2], p.z)), M.m[4 * r + 3]);
 }
-
 // -------------------------------------------------------------------------------------------------------------
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -426,34 +431,27 @@ sicp_status sicp_cloud_get_classes(const sicp_cloud* c, uint32_t* labels_out, in
 }
 
 sicp_status sicp_cloud_transform_f32(const sicp_cloud* c, const double* pose7, void* out_xyz, size_t out_stride) {
-  // Matrix4f path of the finalisation (gicp.hpp:166-171): float matrix, float math, host-side (n*12 B; not on the hot path
-  // of the pose).  The device holds the points in sorted order; fetch them back in original order first.
+  // Matrix4f path of the finalisation (gicp.hpp:166-171, em_icp.hpp:192-197, semantic_point_cloud.hpp:105-111): the pose
+  // is cast to a float 4x4 and applied in float arithmetic, on the device, to the points in the caller's original order.
   SICP_REQUIRE(c && pose7 && out_xyz && out_stride >= 12, "bad argument");
   cudaStream_t st = current_stream();
   SICP_CUDA(cudaSetDevice(c->device));
+  if (c->n == 0) return SICP_OK;
+  double Rd[9];
+  quat_to_R(pose7, Rd);
+  Mat34f M;
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) M.m[4 * i + j] = (float)Rd[3 * i + j]; M.m[4 * i + 3] = (float)pose7[4 + i]; }
   std::vector<float> h(3 * c->n);
   float* d_tmp;
-  SICP_CUDA(cudaMallocAsync(&d_tmp, std::max<size_t>(1, c->n) * 12, st));
-  if (c->nslots) pack_xyz_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->d_pts, c->nslots, d_tmp);
+  SICP_CUDA(cudaMallocAsync(&d_tmp, c->n * 12, st));
+  transform_f32_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->d_pts, c->nslots, M, d_tmp);
+  count_launches(1);
+  SICP_CUDA(cudaGetLastError());
   SICP_CUDA(cudaMemcpyAsync(h.data(), d_tmp, c->n * 12, cudaMemcpyDeviceToHost, st));
   SICP_CUDA(cudaStreamSynchronize(st));
   SICP_CUDA(cudaFreeAsync(d_tmp, st));
-  double Rd[9];
-  {
-    const double x = pose7[0], y = pose7[1], z = pose7[2], w = pose7[3];
-    const double tx = 2 * x, ty = 2 * y, tz = 2 * z, twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x,
-                 tyy = ty * y, tyz = tz * y, tzz = tz * z;
-    Rd[0] = 1 - (tyy + tzz); Rd[1] = txy - twz; Rd[2] = txz + twy; Rd[3] = txy + twz; Rd[4] = 1 - (txx + tzz); Rd[5] = tyz - twx;
-    Rd[6] = txz - twy; Rd[7] = tyz + twx; Rd[8] = 1 - (txx + tyy);
-  }
-  float M[12];
-  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) M[4 * i + j] = (float)Rd[3 * i + j]; M[4 * i + 3] = (float)pose7[4 + i]; }
-  for (size_t i = 0; i < c->n; i++) {
-    const float x = h[3 * i], y = h[3 * i + 1], z = h[3 * i + 2];
-    float o[3];
-    for (int r = 0; r < 3; r++) o[r] = M[4 * r] * x + M[4 * r + 1] * y + M[4 * r + 2] * z + M[4 * r + 3];
-    std::memcpy((char*)out_xyz + i * out_stride, o, 12);
-  }
+  if (out_stride == 12) std::memcpy(out_xyz, h.data(), c->n * 12);
+  else for (size_t i = 0; i < c->n; i++) std::memcpy((char*)out_xyz + i * out_stride, &h[3 * i], 12);
   return SICP_OK;
 }
 

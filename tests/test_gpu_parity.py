@@ -312,3 +312,14 @@ def test_semantic_class_rules(sicp, oracle, pkg):
     res = sicp.register(sicp.ALGO_SEMANTIC, src, tgt, opts, p["init"])
     rot, trans = pkg.synth.pose_error(res["pose"], ref["pose"])
     assert rot < ROT_TOL and trans < TRANS_TOL and res["outer_iter"] == ref["outer_iter"]
+
+
+def test_final_cloud_transform_is_float_matrix_math(sicp, oracle, room):
+    """gicp.hpp:166-171: `trans.matrix().cast<float>()` applied by pcl::transformPointCloud in float arithmetic."""
+    c = sicp.Cloud(room["src_xyz"])
+    pose = room["T_gt"]
+    got = c.transform_f32(pose)
+    M = oracle.se3_matrix(pose).astype(np.float32)  # Eigen toRotationMatrix op sequence, then the float cast
+    x = room["src_xyz"]
+    exp = np.stack([((M[r, 0] * x[:, 0] + M[r, 1] * x[:, 1]) + M[r, 2] * x[:, 2]) + M[r, 3] for r in range(3)], axis=1)
+    assert got.dtype == np.float32 and np.array_equal(got, exp.astype(np.float32))
