@@ -229,6 +229,7 @@ __device__ __forceinline__ void lm_control_warp(LMState& S, const double* tot, i
   double radius = S.radius, decrease = S.decrease_factor, x_norm = S.x_norm, gmax = S.gmax, model = S.model, cost = S.cost;
   int reuse_diag = S.reuse_diag, last_successful = S.last_successful, invalid = S.invalid, iter = S.iter, term = S.term, done = 0;
   const int started = S.started;
+  __syncwarp();  // every lane holds its copy before any lane stores back (the stores are at the end and in the adopt step)
   // ---- iteration zero, or accept / reject the evaluated candidate (uniform)
   int adopt = 0;
   if (!started) {
@@ -678,7 +679,9 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
         return;
       }
       if (threadIdx.x < 32) {
-        if (threadIdx.x == 0 && !S.started) {
+        const int was_started = S.started;
+        __syncwarp();
+        if (threadIdx.x == 0 && !was_started) {
           double* ss = reinterpret_cast<double*>(&S);
           for (int i = 0; i < (int)(sizeof(LMState) / sizeof(double)); i++) ss[i] = 0.0;
           for (int i = 0; i < 7; i++) S.x[i] = s_x[i];

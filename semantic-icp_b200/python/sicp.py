@@ -116,6 +116,7 @@ class Cloud:
         xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
         lab = np.ascontiguousarray(labels, dtype=np.uint32) if labels is not None else None
         self.n = xyz.shape[0]
+        self._N, self._k, self._eps = 0, 20, 1e-3
         self.h = C.c_void_p()
         _check(lib().sicp_cloud_create(_p(xyz), C.c_size_t(12), _p(lab), C.c_size_t(4), C.c_size_t(self.n), C.c_int(layout),
                                        C.c_int(device), C.byref(self.h)))
@@ -124,6 +125,7 @@ class Cloud:
     def from_device(cls, d_xyz_ptr, d_labels_ptr, n, layout=CLOUD_WHOLE, device=0):
         self = cls.__new__(cls)
         self.n = n
+        self._N, self._k, self._eps = 0, 20, 1e-3
         self.h = C.c_void_p()
         _check(lib().sicp_cloud_create_device(C.c_void_p(d_xyz_ptr), C.c_void_p(d_labels_ptr) if d_labels_ptr else None, C.c_size_t(n),
                                               C.c_int(layout), C.c_int(device), C.byref(self.h)))
