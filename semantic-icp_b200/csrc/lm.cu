@@ -367,6 +367,9 @@ __device__ __forceinline__ void lm_control_warp(LMState& S, const double* tot, i
   __syncwarp();
 }
 
+#ifdef SICP_STATS
+static __device__ unsigned long long g_lm_blk[512][2];  // per block: cycles in sweep+reduce, cycles waiting for the next pose (summed over evals)
+#endif
 struct LMArgs {
   CloudView sv;
   LMConfig cfg;
@@ -656,11 +659,15 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
       if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(&sy->count, 1u);
-        if (!eval_only) while ((int)(ld_acquire(&sy->flag) - gen) < 0) __nanosleep(32);
       }
       if (eval_only) return;
-      __syncthreads();
-      if (threadIdx.x < 8) s_x[threadIdx.x] = __ldcg(&sy->bcast[threadIdx.x]);
+      // lanes 0..7 spin on the generation flag (one transaction per poll; no nanosleep: its wake-up granularity is of the
+      // order of a microsecond, longer than the whole control step it would be waiting for) and then fetch their word of
+      // the broadcast record — flag and record share a 128-byte line
+      if (threadIdx.x < 8) {
+        while ((int)(ld_acquire(&sy->flag) - gen) < 0) { }
+        s_x[threadIdx.x] = __ldcg(&sy->bcast[threadIdx.x]);
+      }
       __syncthreads();
       t_wait += clock64() - t0;
     } else {
@@ -726,6 +733,9 @@ __global__ void __launch_bounds__(kLmThreads, 2) lm_kernel(LMArgs a) {
     }
     if (s_x[7] != 0.0) break;
   }
+#ifdef SICP_STATS
+  if (threadIdx.x == 0 && blockIdx.x < 512) { atomicAdd(&g_lm_blk[blockIdx.x][0], (unsigned long long)t_comp); atomicAdd(&g_lm_blk[blockIdx.x][1], (unsigned long long)t_wait); }
+#endif
   if (threadIdx.x == 0 && controller) {  // diagnostics: controller block's sweep / wait / control cycles
     a.ctl->dbg_cycles[0] += t_comp;
     a.ctl->dbg_cycles[1] += t_wait;
@@ -845,3 +855,14 @@ sicp_status launch_fused_labels(const sicp_cloud* src, const sicp_cloud* tgt, do
 }
 
 }  // namespace sicp
+
+extern "C" sicp_status sicp_debug_lm_blocks(unsigned long long* out1024, int reset) {
+#ifdef SICP_STATS
+  SICP_CUDA(cudaDeviceSynchronize());
+  SICP_CUDA(cudaMemcpyFromSymbol(out1024, sicp::g_lm_blk, sizeof(unsigned long long) * 1024));
+  if (reset) { static unsigned long long z[1024] = {0}; SICP_CUDA(cudaMemcpyToSymbol(sicp::g_lm_blk, z, sizeof z)); }
+#else
+  for (int i = 0; i < 1024; i++) out1024[i] = 0;
+#endif
+  return SICP_OK;
+}

@@ -49,3 +49,14 @@ sc, cy = trace(nw)
 describe("self k=20", sc, cy)
 heavy = np.argsort(-cy)[:10]
 print("  heaviest warps:", [(int(i), int(sc[i]), int(cy[i])) for i in heavy])
+
+# LM: per-block sweep / wait cycles (is the controller waiting for slow sweeps or for flag / counter propagation?)
+blk = (C.c_ulonglong * 1024)()
+L.sicp_debug_lm_blocks(blk, C.c_int(1))
+r = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
+L.sicp_debug_lm_blocks(blk, C.c_int(1))
+a = np.array(blk[:], dtype=np.float64).reshape(512, 2)[:296] / r["lm_evals_total"]
+print("LM per block, cycles/eval: sweep+reduce mean %.0f min %.0f p50 %.0f p90 %.0f max %.0f (block 0: %.0f) | wait-for-pose mean %.0f (block 0 waits for arrivals: %.0f)" %
+      (a[1:, 0].mean(), a[1:, 0].min(), np.percentile(a[1:, 0], 50), np.percentile(a[1:, 0], 90), a[1:, 0].max(), a[0, 0], a[1:, 1].mean(), a[0, 1]))
+order = np.argsort(-a[:, 0])[:8]
+print("  slowest blocks:", [(int(b), int(a[b, 0])) for b in order])
