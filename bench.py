@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=8, help="scan pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=16, help="scan pairs per step per GPU")
     ap.add_argument("--points", type=int, default=120_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -293,7 +293,7 @@ def main():
             knn_qps[f"k{k}"] = n * reps / (e0.elapsed_time(e1) * 1e-3)
         s.close(); t.close()
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N=1 only
             r, cores = cpu_oracle_run(p0)
             cpu = {"value": 1.0 / r["seconds"], "unit": "registrations/s", "cores": cores, "kind": "port",
                    "sample": "one full 120k-point EM-ICP registration of pair 0 (oracle restatement, OpenMP all threads)",

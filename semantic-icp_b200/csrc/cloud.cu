@@ -352,6 +352,9 @@ static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, c
   }
   if (rc == SICP_OK) rc = build_cloud(c, d_xyz, d_labels, d_rank, sizes, st);
   if (d_rank) cudaFreeAsync(d_rank, st);
+  if (rc == SICP_OK && (cudaEventCreateWithFlags(&c->built_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(c->built_ev, st) != cudaSuccess)) {
+    set_error("event creation failed"); rc = SICP_ERR_CUDA;
+  }
   if (rc != SICP_OK) { sicp_cloud_destroy(c); return rc; }
   *out = c;
   return SICP_OK;
@@ -409,6 +412,7 @@ void sicp_cloud_destroy(sicp_cloud* c) {
   void* bufs[] = {c->d_slab, c->d_nrm, c->d_avec};
   for (void* b : bufs) if (b) cudaFreeAsync(b, st);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);
+  if (c->built_ev) cudaEventDestroy(c->built_ev);
   delete c;
 }
 

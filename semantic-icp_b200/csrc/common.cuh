@@ -109,5 +109,6 @@ struct sicp_cloud {
   uint32_t min_label = 0, max_label = 0;
   bool label_range_known = false;
   cudaEvent_t ready_ev = nullptr;  // recorded after the last precompute; consumers on other streams wait on it
+  cudaEvent_t built_ev = nullptr;  // recorded after the build (upload, sort, tree); work on other streams waits on it
   sicp::CloudView view() const;
 };

@@ -209,10 +209,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     }
     SICP_CUDA(cudaEventCreate(&fork));
     SICP_CUDA(cudaEventRecord(fork, base));
-    for (int s = 0; s < S; s++) {
-      streams[s] = t_streams[s];
-      SICP_CUDA(cudaStreamWaitEvent(streams[s], fork, 0));
-    }
+    for (int s = 0; s < S; s++) streams[s] = t_streams[s];  // each job waits for ITS clouds (built_ev), not for the whole base stream
   }
   sicp_status rc = SICP_OK;
   const int kChunk = 3;
@@ -231,6 +228,10 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     // covariances / label vectors on this job's stream (no-op when cached); other jobs sharing a cloud wait on its event
     jb.tm.on = jb.opts->profile != 0;
     jb.trace_ref = fork; jb.trace_id = j;
+    if (st != base) {  // the clouds may still be building on the stream that created them
+      if (jb.src->built_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.src->built_ev, 0));
+      if (jb.tgt->built_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.tgt->built_ev, 0));
+    }
     jb.tm.begin(SICP_STAGE_COV, st);
     sicp_set_stream(st);
     sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts);
