@@ -257,17 +257,22 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
 
 // first-appearance class order (pcl_2_semantic.h:24-35) → per-point rank + class sizes
 static sicp_status classify(sicp_cloud* c, const uint32_t* h_labels, size_t n, uint8_t* rank, std::vector<int>* sizes) {
-  std::unordered_map<uint32_t, int> idx;
+  // small labels (the usual case) go through a direct table, anything else through a hash map
+  constexpr uint32_t kDirect = 1u << 16;
+  std::vector<int16_t> direct(kDirect, (int16_t)-1);
+  std::unordered_map<uint32_t, int> sparse;
   for (size_t i = 0; i < n; i++) {
-    auto it = idx.find(h_labels[i]);
+    const uint32_t l = h_labels[i];
     int r;
-    if (it == idx.end()) {
+    if (l < kDirect) r = direct[l];
+    else { auto it = sparse.find(l); r = it == sparse.end() ? -1 : it->second; }
+    if (r < 0) {
       r = (int)c->class_labels.size();
       SICP_REQUIRE(r < 128, "PER_CLASS clouds support at most 128 distinct labels");
-      idx.emplace(h_labels[i], r);
-      c->class_labels.push_back(h_labels[i]);
+      if (l < kDirect) direct[l] = (int16_t)r; else sparse.emplace(l, r);
+      c->class_labels.push_back(l);
       sizes->push_back(0);
-    } else r = it->second;
+    }
     rank[i] = (uint8_t)r;
     (*sizes)[r]++;
   }

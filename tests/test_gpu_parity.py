@@ -323,3 +323,20 @@ def test_final_cloud_transform_is_float_matrix_math(sicp, oracle, room):
     x = room["src_xyz"]
     exp = np.stack([((M[r, 0] * x[:, 0] + M[r, 1] * x[:, 1]) + M[r, 2] * x[:, 2]) + M[r, 3] for r in range(3)], axis=1)
     assert got.dtype == np.float32 and np.array_equal(got, exp.astype(np.float32))
+
+
+def test_class_order_with_large_sparse_labels(sicp, oracle):
+    rng = np.random.default_rng(9)
+    xyz = rng.normal(size=(2000, 3)).astype(np.float32)
+    pool = np.array([4_000_000_000, 7, 65_536, 65_535, 123_456, 0], dtype=np.uint32)   # direct-table and hash-map labels mixed
+    labels = pool[rng.integers(0, len(pool), size=2000)]
+    c = sicp.Cloud(xyz, labels, layout=sicp.CLOUD_PER_CLASS)
+    labs, sizes = c.classes()
+    rl, rs, order = oracle.label_split(labels)
+    assert np.array_equal(labs, rl) and np.array_equal(sizes, np.diff(rs))
+    idx, d2 = sicp.knn(c, xyz[:300], 1, q_labels=labels[:300])
+    for lab in pool:
+        qs = np.nonzero(labels[:300] == lab)[0]
+        ts = np.nonzero(labels == lab)[0]
+        ridx, rd2 = oracle.knn(xyz[ts], xyz[qs], 1)
+        assert np.array_equal(idx[qs, 0], ts[ridx[:, 0]]) and np.array_equal(d2[qs], rd2)
