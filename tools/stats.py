@@ -55,7 +55,8 @@ blk = (C.c_ulonglong * 1024)()
 L.sicp_debug_lm_blocks(blk, C.c_int(1))
 r = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
 L.sicp_debug_lm_blocks(blk, C.c_int(1))
-a = np.array(blk[:], dtype=np.float64).reshape(512, 2)[:296] / r["lm_evals_total"]
+a = np.array(blk[:], dtype=np.float64).reshape(512, 2) / r["lm_evals_total"]
+a = a[: max(1, int(np.count_nonzero(a[:, 0])))]
 print("LM per block, cycles/eval: sweep+reduce mean %.0f min %.0f p50 %.0f p90 %.0f max %.0f (block 0: %.0f) | wait-for-pose mean %.0f (block 0 waits for arrivals: %.0f)" %
       (a[1:, 0].mean(), a[1:, 0].min(), np.percentile(a[1:, 0], 50), np.percentile(a[1:, 0], 90), a[1:, 0].max(), a[0, 0], a[1:, 1].mean(), a[0, 1]))
 order = np.argsort(-a[:, 0])[:8]
