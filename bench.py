@@ -151,7 +151,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     B, n = args.pairs, args.points
-    pairs = [synth.kitti_pair(rank * B + i, n_points=n) for i in range(B)]
+    # every rank registers the SAME B seeded pairs: weak scaling with identical per-GPU work (distinct shards make the
+    # max-over-ranks time a measure of shard-to-shard data variance: 39-47 ms/step across 4 ranks)
+    pairs = [synth.kitti_pair(i, n_points=n) for i in range(B)]
     cm = pairs[0]["cm"]
     opts = sicp.default_options(sicp.ALGO_EM, cm=cm)
     inits = np.stack([p["init"] for p in pairs])
@@ -216,8 +218,13 @@ def main():
         barrier()
         wall = time.perf_counter() - wall0
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        by_rank = [total_ms]
         if world > 1:
+            allt = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            by_rank = [float(x.item()) for x in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.by_rank = by_rank
         return float(t.item()), res, wall
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -225,6 +232,7 @@ def main():
         step_device()
     l0 = sicp.launch_count()
     ms_dev, res_dev, _ = timed(step_device, args.steps, 0, sampler)
+    ms_dev_by_rank = [round(x / args.steps, 3) for x in timed.by_rank]
     launches = sicp.launch_count() - l0
     clocks = sampler.summary() if sampler else None
     ms_e2e, res_e2e, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
@@ -305,14 +313,15 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"KITTI-shaped pairs, {n} pts/scan, 20 classes, confusion-matrix EM-ICP (configs[1])",
-                       "pairs_per_step_per_gpu": B, "algo": "EmIterativeClosestPoint<20>", "k_cov": 20, "k_corr": 4,
+                       "pairs_per_step_per_gpu": B, "shards": "every rank registers the same seeded pairs (identical per-GPU work)",
+                       "algo": "EmIterativeClosestPoint<20>", "k_cov": 20, "k_corr": 4,
                        "l2": "flushed between timed steps (256 MiB memset outside the events); per-step working set > L2",
                        "outer_passes": [r["outer_iter"] for r in res_dev], "lm_iters": [r["lm_iters_total"] for r in res_dev]},
             "e2e": {"value": e2e_v, "unit": "registrations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "records_gathered": int(records.shape[0]), "knn_queries_per_s": knn_qps,
+            "ms_per_step_by_rank": ms_dev_by_rank, "records_gathered": int(records.shape[0]), "knn_queries_per_s": knn_qps,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
