@@ -33,8 +33,12 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <pcl/common/transforms.h>
+#if __has_include(<pcl/io/pcd_io.h>)
+#include <pcl/io/pcd_io.h>
+#endif
 #else
 #include "compat/pcl_min.h"
+#include "compat/pcl_io_min.h"
 #endif
 
 #include <cstddef>

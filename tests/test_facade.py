@@ -81,3 +81,63 @@ def test_facade_matches_oracle(facade_bin, pkg, oracle, tmp_path):
     assert np.allclose(np.array(got["gicp_final0"], dtype=np.float32), exp, atol=1e-5)
     assert got["gicp_src_cov_n"] == len(p["src_xyz"])
     assert got["fused_n"] == len(p["src_xyz"]) and got["fused_same_as_input"] > 0.8 * len(p["src_xyz"])
+
+
+def test_compat_shims_against_golden_se3(tmp_path):
+    """The Eigen / Sophus / PCL stand-ins (facade/compat) on the CPU: layouts, transformPointCloud, SE(3) golden vectors."""
+    with open(os.path.join(ROOT, "tests", "golden", "se3.json")) as f:
+        items = json.load(f)
+    flat = tmp_path / "se3.txt"
+    with open(flat, "w") as f:
+        for it in items:
+            row = list(it["delta"]) + list(it["pose7"]) + list(it["delta_b"]) + list(it["pose7_ab"]) + list(it["pose7_inv"])
+            f.write(" ".join(repr(float(x)) for x in row) + "\n")
+    exe = str(tmp_path / "shim_check")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O1", "-Wall", "-Werror", "-DSICP_FACADE_FORCE_SHIMS", f"-I{ROOT}/semantic-icp_b200/facade",
+                           f"-I{ROOT}/include", os.path.join(ROOT, "tests", "cpp", "shim_check.cc"), "-o", exe])
+    r = subprocess.run([exe, str(flat), str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "shim_check OK" in r.stdout
+
+
+def _write_pcd(path, xyz, labels, binary):
+    n = len(xyz)
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z label\nSIZE 4 4 4 4\nTYPE F F F U\nCOUNT 1 1 1 1\n"
+           f"WIDTH {n}\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS {n}\nDATA {'binary' if binary else 'ascii'}\n")
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        if binary:
+            rec = np.zeros(n, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("l", "<u4")])
+            rec["x"], rec["y"], rec["z"], rec["l"] = xyz[:, 0], xyz[:, 1], xyz[:, 2], labels
+            f.write(rec.tobytes())
+        else:
+            for p, l in zip(xyz, labels):
+                f.write(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r} {int(l)}\n".encode())
+
+
+@pytest.mark.gpu
+def test_example_driver_pcd_to_metrics(pkg, oracle, sicp, tmp_path):
+    """examples/pair_eval.cc: PCD in -> range filter -> EM-ICP + GICP through the facade -> SE(3) errors + label agreement."""
+    p = pkg.synth.room_pair(seed=31, n_points=6000)
+    _write_pcd(tmp_path / "a.pcd", p["src_xyz"], p["src_labels"], binary=True)
+    _write_pcd(tmp_path / "b.pcd", p["tgt_xyz"], p["tgt_labels"], binary=False)
+    np.savetxt(tmp_path / "cm.txt", p["cm"], fmt="%.17g")
+    exe = str(tmp_path / "pair_eval")
+    libdir = os.path.join(ROOT, "semantic-icp_b200", "lib")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++11", "-O2", "-Wall", "-Werror", f"-I{ROOT}/semantic-icp_b200/facade", f"-I{ROOT}/include",
+                           os.path.join(ROOT, "examples", "pair_eval.cc"), "-o", exe, f"-L{libdir}", "-lsicp_b200", f"-Wl,-rpath,{libdir}"])
+    rng_m = 5.5  # drops the far corners of the room
+    r = subprocess.run([exe, str(tmp_path / "a.pcd"), str(tmp_path / "b.pcd"), str(tmp_path / "cm.txt"), str(rng_m)] + [repr(float(v)) for v in p["T_gt"]],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = json.loads(r.stdout)
+    ka, kb = oracle.filter_range(p["src_xyz"], rng_m), oracle.filter_range(p["tgt_xyz"], rng_m)
+    assert got["n_source"] == len(ka) < len(p["src_xyz"]) and got["n_target"] == len(kb)
+    sx, sl, tx, tl = p["src_xyz"][ka], p["src_labels"][ka], p["tgt_xyz"][kb], p["tgt_labels"][kb]
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    for name, ref in (("em", oracle.align_em(sx, sl, tx, tl, p["cm"], ident)), ("gicp", oracle.align_gicp(sx, tx, ident))):
+        rot, trans = pkg.synth.pose_error(np.array(got[name]["pose"]), ref["pose"])
+        assert rot < ROT_TOL and trans < TRANS_TOL and got[name]["outer_iter"] == ref["outer_iter"], (name, rot, trans)
+        assert np.allclose(got[name + "_error"], oracle.pose_errors(p["T_gt"], np.array(got[name]["pose"])), rtol=1e-5, atol=1e-12)
+    la = got["label_agreement"]
+    assert 0.5 < la["accuracy"] <= 1.0 and la["pairs"] == len(ka) and la["mean_distance"] < 0.3
