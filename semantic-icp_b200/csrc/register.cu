@@ -213,9 +213,9 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   }
   sicp_status rc = SICP_OK;
   const int kChunk = 3;
-  // A lone solve takes every SM (2 CTAs each).  Concurrent solves get a quarter of that each: their sweeps are longer,
-  // so the latency-bound control step between sweeps idles a smaller share of the registers they hold, and kNN kernels
-  // of other registrations fit beside them.
+  // A lone solve takes every SM (one CTA each).  Concurrent solves get a quarter of the SMs each: their sweeps are longer,
+  // so the latency-bound control step between sweeps idles a smaller share of the machine, and the kNN kernels of other
+  // registrations run on the SMs no solve occupies.
   int lm_grid = lm_grid_blocks(jobs[0].src->device) / (S > 1 ? 4 : 1);
   if (const char* e = getenv("SICP_LM_GRID")) { const int g = atoi(e); if (g > 0 && S > 1) lm_grid = std::min(g, lm_grid_blocks(jobs[0].src->device)); }
   std::vector<int> slot_job(S, -1);
@@ -283,6 +283,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     for (Job& jb : jobs) for (int i = 0; i < 3; i++) h[i] += jb.host_ms[i];
     fprintf(stderr, "[sicp] host ms inside launches: kNN %.2f E-step %.2f LM %.2f (all jobs)\n", h[0], h[1], h[2]);
   }
+  if (rc != SICP_OK) cudaDeviceSynchronize();  // error path: nothing may still be writing a pinned control block we are about to recycle
   for (Job& jb : jobs) if (!jb.finished && jb.ws.st) jb.ws.release();
   if (S > 1) {
     for (int s = 0; s < S; s++) {
