@@ -134,7 +134,16 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
   const int lane = threadIdx.x & 31;
   const int top = sg.nlevels - 1;
   int sp = 0;
-  constexpr int SEED = (K >= 8) ? 1 : 0;
+#ifndef SICP_SEED_BIG
+#define SICP_SEED_BIG 1
+#endif
+#ifndef SICP_SEED_SMALL
+#define SICP_SEED_SMALL 0
+#endif
+#ifndef SICP_SPLIT_SMALL
+#define SICP_SPLIT_SMALL 2
+#endif
+  constexpr int SEED = (K >= 8) ? SICP_SEED_BIG : SICP_SEED_SMALL;  // Morton neighbours of a home leaf seeded with it (tuned: tools/probe_cov.py A/B)
   const int home = valid ? home_leaf(tv, sg, qx, qy, qz) : -1;
   int myseed = -1;   // lane i remembers the i-th seed leaf
   bool seeded = false;
@@ -236,7 +245,7 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
 #ifdef SICP_STATS
       dbg_scans++;
 #endif
-      constexpr int kSplit = (K >= 8) ? 1 : 2, kPart = kLeaf / kSplit;  // measured: helps short lists (k<=4: -3%), not k = 20
+      constexpr int kSplit = (K >= 8) ? 1 : SICP_SPLIT_SMALL, kPart = kLeaf / kSplit;  // measured: helps short lists (k<=4: -3%), not k = 20
 #pragma unroll 1
       for (int h = 0; h < kSplit; h++) {
         unsigned pass = 0;

@@ -15,7 +15,10 @@
 
 namespace sicp {
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef SICP_WPB
+#define SICP_WPB 4
+#endif
+constexpr int kWarpsPerBlock = SICP_WPB;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
 // ------------------------------------------------------------------ Eigen::JacobiSVD<Matrix3d> restated (U's last column)

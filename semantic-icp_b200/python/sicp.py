@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libsicp_b200.so")
+LIB_PATH = os.environ.get("SICP_LIB") or os.path.join(PKG_ROOT, "lib", "libsicp_b200.so")  # SICP_LIB: A/B builds in tools/
 
 ALGO_GICP, ALGO_SEMANTIC, ALGO_EM = 0, 1, 2
 CLOUD_WHOLE, CLOUD_PER_CLASS = 0, 1
