@@ -22,7 +22,11 @@ namespace cg = cooperative_groups;
 
 namespace sicp {
 
-constexpr int kLmThreads = 256;
+#ifndef SICP_LM_THREADS
+#define SICP_LM_THREADS 256
+#endif
+constexpr int kLmThreads = SICP_LM_THREADS;
+constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kAcc = 28;  // 21 lower-triangular H + 6 g + cost
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -553,16 +557,18 @@ __device__ __forceinline__ void block_reduce(const double* acc, double* s_acc, d
 #pragma unroll
   for (int i = 0; i < kAcc; i++) s_acc[i * kLmThreads + tid] = acc[i];
   __syncthreads();
-  if (tid < kAcc * 8) {
-    const int row = tid >> 3, seg = tid & 7;
+  {  // kAcc * kLmWarps <= kLmThreads (kAcc < 32); every thread runs the shuffles, the surplus ones carry zeros
+    const bool active = tid < kAcc * kLmWarps;
+    const int row = active ? tid / kLmWarps : 0, seg = tid % kLmWarps;
     const double* base = s_acc + row * kLmThreads + seg * 32;
     double s = 0;
+    if (active) {
 #pragma unroll 8
-    for (int k = 0; k < 32; k++) s += base[(k + tid) & 31];
-    s += __shfl_xor_sync(kFullMask, s, 1);
-    s += __shfl_xor_sync(kFullMask, s, 2);
-    s += __shfl_xor_sync(kFullMask, s, 4);
-    if (seg == 0) part[(size_t)blockIdx.x * kAcc + row] = s;
+      for (int k = 0; k < 32; k++) s += base[(k + tid) & 31];
+    }
+#pragma unroll
+    for (int off = 1; off < kLmWarps; off <<= 1) s += __shfl_xor_sync(kFullMask, s, off);  // kLmWarps is a power of two
+    if (active && seg == 0) part[(size_t)blockIdx.x * kAcc + row] = s;
   }
 }
 
@@ -572,11 +578,11 @@ __device__ __forceinline__ void reduce_partials(const double* part, double (*s_r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0;
   if (lane < kAcc) {
-    constexpr int kMaxPerWarp = 40;  // grids of up to 320 blocks
+    constexpr int kMaxPerWarp = 320 / kLmWarps;  // grids of up to 320 blocks
     double v[kMaxPerWarp];
 #pragma unroll
     for (int k = 0; k < kMaxPerWarp; k++) {
-      const int bI = warp + 8 * k;
+      const int bI = warp + kLmWarps * k;
       v[k] = bI < (int)gridDim.x ? __ldcg(&part[(size_t)bI * kAcc + lane]) : 0.0;
     }
 #pragma unroll

@@ -212,7 +212,8 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     for (int s = 0; s < S; s++) streams[s] = t_streams[s];  // each job waits for ITS clouds (built_ev), not for the whole base stream
   }
   sicp_status rc = SICP_OK;
-  const int kChunk = 3;
+  int kChunk = 3;  // passes enqueued between two readbacks of the control block
+  if (const char* e = getenv("SICP_CHUNK")) { const int v = atoi(e); if (v > 0) kChunk = v; }
   // A lone solve takes every SM (one CTA each).  Concurrent solves get a quarter of the SMs each: their sweeps are longer,
   // so the latency-bound control step between sweeps idles a smaller share of the machine, and the kNN kernels of other
   // registrations run on the SMs no solve occupies.
