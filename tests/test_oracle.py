@@ -233,3 +233,25 @@ def test_empty_problem_leaves_pose_unchanged(oracle):
     init = oracle.se3_exp([0.1, 0.2, 0.3, 0.01, 0.02, 0.03])
     r = oracle.align_gicp(src, tgt, init)
     assert np.array_equal(r["pose"], init) and r["outer_iter"] == 1 and r["n_corr_last"] == 0
+
+
+# ------------------------------------------------------------------------------------------------ independent transcription
+def test_align_matches_independent_numpy_transcription(oracle, pkg):
+    """tests/golden/align_small.json comes from tests/golden/numpy_reference.py — a separate numpy restatement of the
+    reference's align() loops (numpy.linalg / scipy Rotation routes, closed-form Jacobian, brute-force kNN) that shares
+    no code with the oracle.  Same pass counts, same LM iterations per pass, same pose."""
+    with open(os.path.join(GOLD, "align_small.json")) as f:
+        cases = json.load(f)
+    assert {c["algo"] for c in cases} == {"gicp", "em", "semantic"}
+    for c in cases:
+        p = pkg.synth.room_pair(seed=c["seed"], n_points=c["n_points"], N=c["N"])
+        if c["algo"] == "gicp":
+            r = oracle.align_gicp(p["src_xyz"], p["tgt_xyz"], p["init"])
+        elif c["algo"] == "em":
+            r = oracle.align_em(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["init"])
+        else:
+            r = oracle.align_semantic(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["init"])
+        assert r["outer_iter"] == c["outer_iter"], c["algo"]
+        assert [int(v) for v in r["pass_lm_iters"]] == c["lm_iters"], c["algo"]
+        rot, trans = pkg.synth.pose_error(r["pose"], np.array(c["pose7"]))
+        assert rot < 1e-7 and trans < 1e-9, (c["algo"], rot, trans)
