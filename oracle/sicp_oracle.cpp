@@ -800,15 +800,18 @@ int orc_num_threads() {
 void orc_knn(const float* tgt, int nt, const float* q, int nq, int k, int32_t* idx, float* d2, int brute, int threads) {
   KdTree tree;
   if (!brute) tree.build(tgt, nt);
-#pragma omp parallel for schedule(dynamic, 64) num_threads(threads > 0 ? threads : 1)
-  for (int i = 0; i < nq; i++) {
-    std::vector<Cand> buf(k);
-    int nn = 0;
-    if (brute) knn_brute(tgt, nt, q + 3 * (size_t)i, k, buf.data(), &nn);
-    else tree.knn(q + 3 * (size_t)i, k, buf.data(), &nn);
-    for (int j = 0; j < k; j++) {
-      idx[(size_t)i * k + j] = j < nn ? buf[j].i : -1;
-      d2[(size_t)i * k + j] = j < nn ? buf[j].d : std::numeric_limits<float>::infinity();
+#pragma omp parallel num_threads(threads > 0 ? threads : 1)
+  {
+    std::vector<Cand> buf(k);  // one scratch list per thread
+#pragma omp for schedule(dynamic, 1024)
+    for (int i = 0; i < nq; i++) {
+      int nn = 0;
+      if (brute) knn_brute(tgt, nt, q + 3 * (size_t)i, k, buf.data(), &nn);
+      else tree.knn(q + 3 * (size_t)i, k, buf.data(), &nn);
+      for (int j = 0; j < k; j++) {
+        idx[(size_t)i * k + j] = j < nn ? buf[j].i : -1;
+        d2[(size_t)i * k + j] = j < nn ? buf[j].d : std::numeric_limits<float>::infinity();
+      }
     }
   }
 }
