@@ -102,10 +102,15 @@ __global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, doubl
       const double kappa = 1.0 - eps;
       apply_Minv(nt, m, d, kappa, b);
       const double mahal = -0.5 * (d[0] * b[0] + d[1] * b[1] + d[2] * b[2]);
-      const double two_pi = 6.283185307179586;
-      const double det2pi = (two_pi * two_pi * two_pi) * det_S(nt, m, kappa);
-      const double density = pow(det2pi, -0.5) * exp(mahal);
-      if (density == 0.0) prob *= 0.0;  // NaN stays "true" like the bool conversion
+      // The density can only underflow to exactly 0 when exp(mahal) is near the bottom of the double range:
+      // det(2 pi S) <= (2 pi)^3 * 8, so the pow factor is >= 0.022 and for mahal > -700 the product is >= 1e-306.
+      // Only candidates beyond that (Mahalanobis^2 > 1400) pay for the pow / exp of the reference expression.
+      if (!(mahal > -700.0)) {
+        const double two_pi = 6.283185307179586;
+        const double det2pi = (two_pi * two_pi * two_pi) * det_S(nt, m, kappa);
+        const double density = pow(det2pi, -0.5) * exp(mahal);
+        if (density == 0.0) prob *= 0.0;  // NaN stays "true" like the bool conversion
+      }
       w = prob;
     }
   }
@@ -143,6 +148,50 @@ struct LMSync {
 enum { TERM_NO_CONV = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_RADIUS = 4, TERM_FAIL = 5 };
 
 __device__ __forceinline__ int tri(int a, int b) { return a >= b ? a * (a + 1) / 2 + b : b * (b + 1) / 2 + a; }
+
+// ---- branch-free FP64 special functions for the sweep.  The library versions carry slow-path subroutine calls for
+// denormal / infinite / negative arguments, which split the residual code into many basic blocks and stop the
+// compiler from interleaving independent residuals; here the arguments are known to be normal and positive
+// (sum >= 1, v >= 2.2e-16, det in (0, 4]), so a MUFU seed + two Newton steps (full double accuracy) is enough.
+__device__ __forceinline__ double rcp_pos(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  return fma(x, e, x);
+}
+__device__ __forceinline__ double rsqrt_pos(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double h = 0.5 * a;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+// log(x) for normal x >= 1 (fdlibm e_log.c reduction and minimax coefficients; error < 1 ulp)
+__device__ __forceinline__ double log_ge1(double x) {
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int k = (hi >> 20) - 1023;
+  hi &= 0x000fffff;
+  const int i = (hi + 0x95f64) & 0x100000;       // mantissa above sqrt(2): halve it, bump the exponent
+  k += i >> 20;
+  const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
+  const double f = m - 1.0;
+  const double sden = rcp_pos(2.0 + f);
+  const double ss = f * sden;
+  const double z = ss * ss;
+  const double w = z * z;
+  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
+  const double t2 = z * (6.666666666666735130e-01 + w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
+  const double R = t2 + t1;
+  const double hfsq = 0.5 * f * f;
+  const double dk = (double)k;
+  // log(1+f) = f - (hfsq - s*(hfsq+R));  log(x) = k*ln2_hi + (log(1+f) + k*ln2_lo)
+  return dk * 6.93147180369123816490e-01 - ((hfsq - (ss * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
 
 // T * exp(delta) (local_parameterization_se3.h:22) on the LM critical path: one sincos, reciprocal multiplies and an
 // rsqrt renormalisation instead of the divisions / square roots of the general-purpose se3.cuh routines.
@@ -298,7 +347,7 @@ __device__ __forceinline__ void lm_control_warp(LMState& S, const double* tot, i
     for (int j = 0; j < 6; j++) {
       const double piv = __shfl_sync(kFullMask, A[j], j);
       ok = ok && (piv > 0);
-      inv[j] = rsqrt(piv);
+      inv[j] = rsqrt_pos(piv);  // pivots of an accepted factorisation are positive normal numbers; otherwise `ok` is false
       Lr[j] = A[j] * inv[j];
 #pragma unroll
       for (int k = j + 1; k < 6; k++) A[k] -= Lr[j] * __shfl_sync(kFullMask, Lr[j], k);
@@ -394,50 +443,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// ---- branch-free FP64 special functions for the sweep.  The library versions carry slow-path subroutine calls for
-// denormal / infinite / negative arguments, which split the residual code into many basic blocks and stop the
-// compiler from interleaving independent residuals; here the arguments are known to be normal and positive
-// (sum >= 1, v >= 2.2e-16, det in (0, 4]), so a MUFU seed + two Newton steps (full double accuracy) is enough.
-__device__ __forceinline__ double rcp_pos(double a) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  double e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  return fma(x, e, x);
-}
-__device__ __forceinline__ double rsqrt_pos(double a) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  const double h = 0.5 * a;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  return fma(y, e, y);
-}
-// log(x) for normal x >= 1 (fdlibm e_log.c reduction and minimax coefficients; error < 1 ulp)
-__device__ __forceinline__ double log_ge1(double x) {
-  int hi = __double2hiint(x);
-  const int lo = __double2loint(x);
-  int k = (hi >> 20) - 1023;
-  hi &= 0x000fffff;
-  const int i = (hi + 0x95f64) & 0x100000;       // mantissa above sqrt(2): halve it, bump the exponent
-  k += i >> 20;
-  const double m = __hiloint2double(hi | (i ^ 0x3ff00000), lo);
-  const double f = m - 1.0;
-  const double sden = rcp_pos(2.0 + f);
-  const double ss = f * sden;
-  const double z = ss * ss;
-  const double w = z * z;
-  const double t1 = w * (3.999999999940941908e-01 + w * (2.222219843214978396e-01 + w * 1.531383769920937332e-01));
-  const double t2 = z * (6.666666666666735130e-01 + w * (2.857142874366239149e-01 + w * (1.818357216161805012e-01 + w * 1.479819860511658591e-01)));
-  const double R = t2 + t1;
-  const double hfsq = 0.5 * f * f;
-  const double dk = (double)k;
-  // log(1+f) = f - (hfsq - s*(hfsq+R));  log(x) = k*ln2_hi + (log(1+f) + k*ln2_lo)
-  return dk * 6.93147180369123816490e-01 - ((hfsq - (ss * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
 }
 
 // rho(s), rho'(s) at s = res^2 of the three Ceres loss compositions, multiplied by the weight w (the
