@@ -103,8 +103,8 @@ uint64_t sicp_launch_count(void);
 /* ---- clouds -------------------------------------------------------------------------------------------------
  * sicp_cloud_create replaces GICP::setSourceCloud/setTargetCloud (gicp.h:42-63), Em...::set*Cloud
  * (em_icp.h:50-66) [layout WHOLE] and pcl_2_semantic + SemanticPointCloud::addSemanticCloud's kd-tree build
- * (pcl_2_semantic.h:14-42, impl/semantic_point_cloud.hpp:17-23) [layout PER_CLASS]: it uploads the points into
- * device SoA buffers and builds the Morton-sorted search tree(s).  xyz points to the first x; consecutive points
+ * (pcl_2_semantic.h:14-42, impl/semantic_point_cloud.hpp:17-23) [layout PER_CLASS: the first-appearance label
+ * partition runs on the device]: it uploads the points into device SoA buffers and builds the Morton-sorted search tree(s).  xyz points to the first x; consecutive points
  * are xyz_stride bytes apart (12 packed, 16 pcl::PointXYZ, 32 pcl::PointXYZL).  labels may be NULL (GICP).     */
 sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* labels, size_t label_stride, size_t n,
                               int layout, int device, sicp_cloud** out);

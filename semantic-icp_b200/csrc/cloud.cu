@@ -7,7 +7,6 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
-#include <unordered_map>
 #include "common.cuh"
 #include "knn.cuh"
 #include "se3.cuh"
@@ -255,28 +254,85 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
   return SICP_OK;
 }
 
-// first-appearance class order (pcl_2_semantic.h:24-35) → per-point rank + class sizes
-static sicp_status classify(sicp_cloud* c, const uint32_t* h_labels, size_t n, uint8_t* rank, std::vector<int>* sizes) {
-  // small labels (the usual case) go through a direct table, anything else through a hash map
-  constexpr uint32_t kDirect = 1u << 16;
-  std::vector<int16_t> direct(kDirect, (int16_t)-1);
-  std::unordered_map<uint32_t, int> sparse;
-  for (size_t i = 0; i < n; i++) {
-    const uint32_t l = h_labels[i];
-    int r;
-    if (l < kDirect) r = direct[l];
-    else { auto it = sparse.find(l); r = it == sparse.end() ? -1 : it->second; }
-    if (r < 0) {
-      r = (int)c->class_labels.size();
-      SICP_REQUIRE(r < 128, "PER_CLASS clouds support at most 128 distinct labels");
-      if (l < kDirect) direct[l] = (int16_t)r; else sparse.emplace(l, r);
-      c->class_labels.push_back(l);
-      sizes->push_back(0);
-    }
-    rank[i] = (uint8_t)r;
-    (*sizes)[r]++;
+// ---- first-appearance class order (pcl_2_semantic.h:24-35) on the device -------------------------------------------
+// The reference walks the cloud once and opens a new class the first time it meets a label; classes are then used in
+// that order.  Here every point inserts its label into a small open-addressing table (64-bit CAS on (1<<32 | label)),
+// takes the atomic minimum of the point index per label (= first appearance) and counts; the host sorts the <= 128
+// table entries by first appearance and a second kernel maps every point to its class rank.  Only the 6 KB table
+// crosses the bus.
+constexpr int kClassSlots = 512;
+struct ClassTable {
+  unsigned long long key[kClassSlots];  // 0 = empty, else (1 << 32) | label
+  unsigned first[kClassSlots];          // smallest original index with this label
+  unsigned count[kClassSlots];
+  unsigned overflow;                    // more distinct labels than slots
+  unsigned pad;
+};
+__device__ __forceinline__ unsigned label_hash(uint32_t l) { return (l * 2654435761u) >> 23; }  // top 9 bits -> [0, 512)
+__global__ void classify_count_kernel(const uint32_t* __restrict__ labels, int n, ClassTable* tab, uint16_t* __restrict__ slot_of_point) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t l = labels[i];
+  const unsigned long long k = (1ull << 32) | l;
+  unsigned h = label_hash(l);
+  int probes = 0;
+  for (;; h = (h + 1) & (kClassSlots - 1)) {
+    const unsigned long long prev = atomicCAS(&tab->key[h], 0ull, k);
+    if (prev == 0ull || prev == k) break;
+    if (++probes >= kClassSlots) { tab->overflow = 1; slot_of_point[i] = 0; return; }
   }
-  return SICP_OK;
+  atomicMin(&tab->first[h], (unsigned)i);
+  atomicAdd(&tab->count[h], 1u);
+  slot_of_point[i] = (uint16_t)h;
+}
+__global__ void classify_rank_kernel(const uint16_t* __restrict__ slot_of_point, int n, const uint8_t* __restrict__ rank_of_slot, uint8_t* __restrict__ rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rank[i] = rank_of_slot[slot_of_point[i]];
+}
+// d_labels: n packed labels on the device.  Fills c->class_labels / *sizes (first-appearance order) and *d_rank_out.
+static sicp_status classify_device(sicp_cloud* c, const uint32_t* d_labels, size_t n, uint8_t** d_rank_out, std::vector<int>* sizes, cudaStream_t st) {
+  *d_rank_out = nullptr;
+  if (n == 0) return SICP_OK;
+  ClassTable* d_tab = nullptr; uint16_t* d_slot = nullptr; uint8_t* d_ros = nullptr;
+  PinnedBlock pb{nullptr, 0, nullptr};
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMallocAsync(&d_tab, sizeof(ClassTable), st));
+    SICP_CUDA(cudaMallocAsync(&d_slot, sizeof(uint16_t) * n, st));
+    SICP_CUDA(cudaMallocAsync(&d_ros, kClassSlots, st));
+    SICP_CUDA(cudaMallocAsync(d_rank_out, n, st));
+    SICP_CUDA(cudaMemsetAsync(d_tab, 0, sizeof(ClassTable), st));
+    SICP_CUDA(cudaMemsetAsync(d_tab->first, 0xff, sizeof(unsigned) * kClassSlots, st));
+    classify_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_labels, (int)n, d_tab, d_slot);
+    char* stage = (char*)pinned_stage(sizeof(ClassTable) + kClassSlots, st, &pb);
+    if (!stage) { set_error("pinned staging allocation failed"); return SICP_ERR_CUDA; }
+    ClassTable* h = (ClassTable*)stage;
+    uint8_t* h_ros = (uint8_t*)(stage + sizeof(ClassTable));
+    SICP_CUDA(cudaMemcpyAsync(h, d_tab, sizeof(ClassTable), cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    SICP_REQUIRE(!h->overflow, "PER_CLASS clouds support at most 128 distinct labels");
+    std::vector<int> used;
+    for (int s = 0; s < kClassSlots; s++) if (h->key[s]) used.push_back(s);
+    SICP_REQUIRE(used.size() <= 128, "PER_CLASS clouds support at most 128 distinct labels");
+    std::sort(used.begin(), used.end(), [&](int x, int y) { return h->first[x] < h->first[y]; });
+    std::memset(h_ros, 0, kClassSlots);
+    for (size_t r = 0; r < used.size(); r++) {
+      h_ros[used[r]] = (uint8_t)r;
+      c->class_labels.push_back((uint32_t)(h->key[used[r]] & 0xffffffffull));
+      sizes->push_back((int)h->count[used[r]]);
+    }
+    SICP_CUDA(cudaMemcpyAsync(d_ros, h_ros, kClassSlots, cudaMemcpyHostToDevice, st));
+    classify_rank_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_slot, (int)n, d_ros, *d_rank_out);
+    count_launches(2);
+    SICP_CUDA(cudaGetLastError());
+    return SICP_OK;
+  };
+  const sicp_status rc = body();
+  if (pb.p) pinned_release(pb, st);
+  if (d_tab) cudaFreeAsync(d_tab, st);
+  if (d_slot) cudaFreeAsync(d_slot, st);
+  if (d_ros) cudaFreeAsync(d_ros, st);
+  if (rc != SICP_OK && *d_rank_out) { cudaFreeAsync(*d_rank_out, st); *d_rank_out = nullptr; }
+  return rc;
 }
 
 static sicp_status init_device(int device) {
@@ -336,20 +392,8 @@ static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, c
   std::vector<int> sizes;
   uint8_t* d_rank = nullptr;
   sicp_status rc = SICP_OK;
-  if (layout == SICP_CLOUD_PER_CLASS) {
-    PinnedBlock pb;
-    uint8_t* rank = (uint8_t*)pinned_stage(std::max<size_t>(n, 1), st, &pb);
-    std::vector<uint32_t> packed(n);
-    for (size_t i = 0; i < n; i++) std::memcpy(&packed[i], (const char*)h_labels + i * label_stride, 4);
-    if (!rank) { set_error("pinned staging allocation failed"); rc = SICP_ERR_CUDA; }
-    if (rc == SICP_OK) rc = classify(c, packed.data(), n, rank, &sizes);
-    if (rc == SICP_OK && n > 0) {
-      if (cudaMallocAsync(&d_rank, n, st) != cudaSuccess || cudaMemcpyAsync(d_rank, rank, n, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-        set_error("rank upload failed"); rc = SICP_ERR_CUDA;
-      }
-    }
-    if (rank) pinned_release(pb, st);
-  } else sizes.push_back((int)n);
+  if (layout == SICP_CLOUD_PER_CLASS) rc = classify_device(c, d_labels, n, &d_rank, &sizes, st);
+  else sizes.push_back((int)n);
   if (rc == SICP_OK && h_labels && n) {  // host-side label range (labels must be 1..N for EM, em_icp.hpp:301)
     uint32_t lo = 0xffffffffu, hi = 0;
     for (size_t i = 0; i < n; i++) { uint32_t l; std::memcpy(&l, (const char*)h_labels + i * label_stride, 4); lo = std::min(lo, l); hi = std::max(hi, l); }
@@ -401,13 +445,7 @@ sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_label
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || layout == SICP_CLOUD_PER_CLASS, "bad layout");
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || d_labels, "PER_CLASS layout needs labels");
   SICP_CHECK(init_device(device));
-  std::vector<uint32_t> h_lab;
-  if (layout == SICP_CLOUD_PER_CLASS && n) {  // the class order is a host-side decision: fetch the labels once
-    h_lab.resize(n);
-    SICP_CUDA(cudaMemcpyAsync(h_lab.data(), d_labels, n * 4, cudaMemcpyDeviceToHost, current_stream()));
-    SICP_CUDA(cudaStreamSynchronize(current_stream()));
-  }
-  return create_common(d_xyz, d_labels, h_lab.empty() ? nullptr : h_lab.data(), 4, n, layout, device, out);
+  return create_common(d_xyz, d_labels, nullptr, 4, n, layout, device, out);
 }
 
 void sicp_cloud_destroy(sicp_cloud* c) {

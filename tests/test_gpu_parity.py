@@ -340,3 +340,27 @@ def test_class_order_with_large_sparse_labels(sicp, oracle):
         ts = np.nonzero(labels == lab)[0]
         ridx, rd2 = oracle.knn(xyz[ts], xyz[qs], 1)
         assert np.array_equal(idx[qs, 0], ts[ridx[:, 0]]) and np.array_equal(d2[qs], rd2)
+
+
+def test_class_partition_on_device(sicp, oracle, room):
+    """pcl_2_semantic.h:24-35 on the device: first-appearance class order, class sizes, too many classes."""
+    import torch
+
+    p = room
+    dx = torch.from_numpy(np.ascontiguousarray(p["src_xyz"])).cuda()
+    dl = torch.from_numpy(p["src_labels"].astype(np.int32)).cuda()
+    torch.cuda.synchronize()
+    c = sicp.Cloud.from_device(dx.data_ptr(), dl.data_ptr(), len(p["src_xyz"]), layout=sicp.CLOUD_PER_CLASS)
+    labs, sizes = c.classes()
+    rl, rs, _ = oracle.label_split(p["src_labels"])
+    assert np.array_equal(labs, rl) and np.array_equal(sizes, np.diff(rs))
+    c.precompute(20, 1e-3)
+    ref = oracle.covariances_per_class(p["src_xyz"], p["src_labels"], 20, 1e-3)
+    assert np.array_equal(c.normals(), ref["normals"])            # device-input cloud == host-input cloud == oracle
+    rng = np.random.default_rng(2)
+    xyz = rng.normal(size=(3000, 3)).astype(np.float32)
+    ok = sicp.Cloud(xyz, (np.arange(3000) % 128 + 5).astype(np.uint32), layout=sicp.CLOUD_PER_CLASS)   # exactly 128 classes
+    assert len(ok.classes()[0]) == 128
+    for nclass in (129, 700):                                       # over the class limit / over the table size
+        with pytest.raises(sicp.SicpError, match="at most 128"):
+            sicp.Cloud(xyz, (np.arange(3000) % nclass).astype(np.uint32) * 977, layout=sicp.CLOUD_PER_CLASS)
