@@ -1,6 +1,7 @@
 // lm.cu — E-step weights (K3) and the device-side M-step (K4 + K5): analytic SE(3) residual/Jacobian evaluation,
-// warp-shuffle reduction of J^T J (21) + J^T r (6) + cost (1), and a Ceres-mirroring Levenberg-Marquardt loop that
-// runs entirely inside ONE cooperative kernel per outer pass (no host round trips inside an inner solve).
+// fixed-order reduction of J^T J (21) + J^T r (6) + cost (1), and a Ceres-mirroring Levenberg-Marquardt loop that
+// runs entirely inside ONE cooperative kernel per outer pass (no host round trips inside an inner solve): every CTA
+// sweeps its share of the residuals, a controller CTA sums the partials, takes the LM decision and publishes the next pose.
 //
 // Replaces: GICPCostFunction::Evaluate/Probability (gicp_cost_function.h:27-87), LocalParameterizationSE3
 // (local_parameterization_se3.h:17-36), SQLoss (sqloss.h:11-19) + the Ceres loss compositions at
@@ -11,14 +12,12 @@
 // Covariances are never materialised: C = I - (1-eps) n n^T, so
 //   C_t + R C_s R^T = 2I - kappa (n_t n_t^T + m m^T),  m = R n_s,  kappa = 1 - eps
 // is inverted in closed form (rank-2 Woodbury), and the 6-dof Jacobian of r = d^T M d for T*exp(delta) is
-//   J_upsilon = -2 c,   J_omega = 2 c x (p_s + C_s c),   c = R^T M d           (verified vs the 1x7 route).
-#include <cooperative_groups.h>
+//   J_upsilon = -2 c,   J_omega = 2 c x (p_s + C_s c),   c = R^T M d           (verified vs the 1x7 route);
+// the sweep evaluates it in the target frame and the rotation is applied once to the reduced totals (see sweep_acc).
 #include <cfloat>
 #include "common.cuh"
 #include "kernels.h"
 #include "se3.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace sicp {
 
