@@ -181,7 +181,7 @@ sicp_status sicp_cloud_transform_f32(const sicp_cloud* cloud, const double* pose
 sicp_status sicp_label_agreement(const sicp_cloud* src, const sicp_cloud* tgt, const double* pose7, double gate_d2, int n_labels,
                                  int64_t* confusion_out, double* stats3_out, uint32_t* pairs_out);
 /* SE(3) error of estimates against ground truth (exec/kitti_metrics.h:31-37): diff = GT * est^-1,
- * err3s[3*i..] = { |log(diff)|^2, |log_SO3(diff)|^2, |translation(diff)|^2 }.  Host arithmetic (a few hundred flops per pose). */
+ * err3s[3*i..] = { |log(diff)|^2, |log_SO3(diff)|^2, |translation(diff)|^2 }, one device thread per pose pair. */
 sicp_status sicp_pose_errors(size_t n, const double* gt7s, const double* est7s, double* err3s);
 /* Range filter of a raw scan (exec/filter_range.h:6-18, used at exec/kitti_eval.cc:124-127): indices (ascending) of the
  * points with x*x+y*y+z*z <= range^2 (float products and sums like the reference), replacing its O(n^2) erase loop. */

@@ -56,6 +56,18 @@ __global__ void label_agreement_kernel(CloudView sv, CloudView tv, const int* __
   }
 }
 
+// one thread per pose pair: diff = GT * est^-1 and its three squared norms (exec/kitti_metrics.h:33-37)
+__global__ void pose_error_kernel(const double* __restrict__ gt7s, const double* __restrict__ est7s, size_t n, double* __restrict__ err3s) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Pose d = pose_mul(pose_from7(gt7s + 7 * i), pose_inv(pose_from7(est7s + 7 * i)));
+  double lg[6];
+  pose_log(d, lg);
+  err3s[3 * i] = lg[0] * lg[0] + lg[1] * lg[1] + lg[2] * lg[2] + lg[3] * lg[3] + lg[4] * lg[4] + lg[5] * lg[5];
+  err3s[3 * i + 1] = lg[3] * lg[3] + lg[4] * lg[4] + lg[5] * lg[5];
+  err3s[3 * i + 2] = d.t[0] * d.t[0] + d.t[1] * d.t[1] + d.t[2] * d.t[2];
+}
+
 // exec/filter_range.h:12: keep iff !((x*x + y*y + z*z) > range*range), products and sums in float, comparison in double
 __global__ void range_flag_kernel(const float* __restrict__ xyz, size_t n, double range2, uint8_t* __restrict__ flags, uint32_t* __restrict__ iota) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,15 +139,29 @@ sicp_status sicp_label_agreement(const sicp_cloud* src, const sicp_cloud* tgt, c
 // exec/kitti_metrics.h:31-37: diff = GT * est^-1;  err3 = { |log(diff)|^2, |log_SO3(diff)|^2, |translation(diff)|^2 }
 sicp_status sicp_pose_errors(size_t n, const double* gt7s, const double* est7s, double* err3s) {
   SICP_REQUIRE((gt7s && est7s && err3s) || n == 0, "null argument");
-  for (size_t i = 0; i < n; i++) {
-    const Pose d = pose_mul(pose_from7(gt7s + 7 * i), pose_inv(pose_from7(est7s + 7 * i)));
-    double lg[6];
-    pose_log(d, lg);
-    err3s[3 * i] = lg[0] * lg[0] + lg[1] * lg[1] + lg[2] * lg[2] + lg[3] * lg[3] + lg[4] * lg[4] + lg[5] * lg[5];
-    err3s[3 * i + 1] = lg[3] * lg[3] + lg[4] * lg[4] + lg[5] * lg[5];
-    err3s[3 * i + 2] = d.t[0] * d.t[0] + d.t[1] * d.t[1] + d.t[2] * d.t[2];
-  }
-  return SICP_OK;
+  if (n == 0) return SICP_OK;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { set_error("no CUDA device available (libsicp_b200 has no CPU fallback)"); return SICP_ERR_CUDA; }
+  cudaStream_t st = current_stream();
+  double *d_gt = nullptr, *d_est = nullptr, *d_err = nullptr;
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMallocAsync(&d_gt, 56 * n, st));
+    SICP_CUDA(cudaMallocAsync(&d_est, 56 * n, st));
+    SICP_CUDA(cudaMallocAsync(&d_err, 24 * n, st));
+    SICP_CUDA(cudaMemcpyAsync(d_gt, gt7s, 56 * n, cudaMemcpyHostToDevice, st));
+    SICP_CUDA(cudaMemcpyAsync(d_est, est7s, 56 * n, cudaMemcpyHostToDevice, st));
+    pose_error_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_gt, d_est, n, d_err);
+    count_launches(1);
+    SICP_CUDA(cudaGetLastError());
+    SICP_CUDA(cudaMemcpyAsync(err3s, d_err, 24 * n, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    return SICP_OK;
+  };
+  const sicp_status rc = body();
+  if (d_gt) cudaFreeAsync(d_gt, st);
+  if (d_est) cudaFreeAsync(d_est, st);
+  if (d_err) cudaFreeAsync(d_err, st);
+  return rc;
 }
 
 sicp_status sicp_filter_range(const void* xyz, size_t xyz_stride, size_t n, double range, int device, uint32_t* keep_idx_out, size_t* n_keep_out) {

@@ -55,8 +55,11 @@ class EmIterativeClosestPoint {
     final_transformation_ = detail::pose7_to_se3(res.pose7);
     outer_iter = res.outer_iter;
     if (finalCloud != nullptr) {  // impl/em_icp.hpp:192-198
-      Eigen::Matrix4f mat = final_transformation_.matrix().template cast<float>();
-      pcl::transformPointCloud(*source_cloud_, *finalCloud, mat);
+      // the float-matrix transform runs on the device (sicp_cloud_transform_f32); every other field of the points
+      // (labels, padding) is carried over from the source, like pcl::transformPointCloud does
+      if (finalCloud.get() != source_cloud_.get()) *finalCloud = *source_cloud_;
+      if (!finalCloud->points.empty())
+        detail::check(sicp_cloud_transform_f32(source_kd_tree_->handle().get(), res.pose7, &finalCloud->points[0].x, sizeof(PointT)), "final cloud transform");
     }
   }
   // impl/em_icp.hpp:202-268: appends the source points, relabelled with the arg-max fused class, to labeledCloud

@@ -71,8 +71,11 @@ class GICP {
     outer_iter = res.outer_iter;
     sourceCovStale_ = targetCovStale_ = true;
     if (finalCloud != nullptr) {  // impl/gicp.hpp:166-172: Matrix4f (float) transform of the source
-      Eigen::Matrix4f mat = finalTransformation_.matrix().template cast<float>();
-      pcl::transformPointCloud(*sourceCloud_, *finalCloud, mat);
+      // the float-matrix transform runs on the device (sicp_cloud_transform_f32); every other field of the points
+      // (labels, padding) is carried over from the source, like pcl::transformPointCloud does
+      if (finalCloud.get() != sourceCloud_.get()) *finalCloud = *sourceCloud_;
+      if (!finalCloud->points.empty())
+        detail::check(sicp_cloud_transform_f32(sourceKdTree_->handle().get(), res.pose7, &finalCloud->points[0].x, sizeof(PointT)), "final cloud transform");
     }
   }
   Sophus::SE3d getFinalTransFormation() { return finalTransformation_; }  // gicp.h:98 (sic)

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 
-def test_pose_errors_match_oracle(sicp, oracle):  # host arithmetic of the library: runs without a GPU
+@pytest.mark.gpu
+def test_pose_errors_match_oracle(sicp, oracle):
     rng = np.random.default_rng(5)
     gt = np.stack([oracle.se3_exp(rng.normal(size=6) * s) for s in (1e-6, 1e-3, 0.1, 1.0, 2.5)])
     est = np.stack([oracle.se3_plus(g, rng.normal(size=6) * 1e-2) for g in gt])
