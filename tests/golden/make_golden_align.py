@@ -29,3 +29,10 @@ for algo, seed, n in (("gicp", 41, 400), ("em", 42, 350), ("semantic", 43, 1700)
 with open(os.path.join(HERE, "align_small.json"), "w") as f:
     json.dump(cases, f, indent=1)
 print("wrote align_small.json")
+
+# getFusedLabels on a small pair (labels + the margin between the two best classes, to recognise exact ties)
+p = pkg.synth.room_pair(seed=45, n_points=400)
+lab, margin = ref.fused_labels(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["T_gt"])
+with open(os.path.join(HERE, "fused_small.json"), "w") as f:
+    json.dump(dict(seed=45, n_points=400, labels=[int(x) for x in lab], margin=[float(x) for x in margin]), f)
+print("wrote fused_small.json")

@@ -274,3 +274,31 @@ def align_semantic(sxyz, slab, txyz, tlab, init7, k=20, eps=1e-3):
         return out
 
     return _outer(build, 1, init7, 1e-3, 35, semantic=True)
+
+
+# ---------------------------------------------------------------- getFusedLabels (impl/em_icp.hpp:202-268)
+def fused_labels(sxyz, slab, txyz, tlab, cm, pose7, k=20, eps=1e-3):
+    N = cm.shape[0]
+    scov, sdist = covariances(sxyz, k, eps, slab, N)
+    tcov, tdist = covariances(txyz, k, eps, tlab, N)
+    R, t = pose7_to_Rt(np.asarray(pose7, dtype=np.float64))
+    idx, d2 = knn(txyz, transform_points(R, t, sxyz), 4)
+    out = np.zeros(len(sxyz), dtype=np.uint32)
+    margin = np.zeros(len(sxyz))
+    for i in range(len(sxyz)):
+        sprob = np.zeros(N)
+        for c in range(4):
+            j = idx[i, c]
+            if j < 0 or not float(d2[i, c]) < 250:
+                continue
+            gate = 1.0 if probability_is_nonzero(R, t, sxyz[i].astype(np.float64), txyz[j].astype(np.float64), scov[i], tcov[j]) else 0.0
+            for s in range(N):
+                sprob[s] += (tdist[j] @ cm[:, s]) * (sdist[i] @ cm[:, s]) * gate
+        best, best_s = 0.0, 0
+        for s in range(N):                                                              # first strict maximum (:256-262)
+            if sprob[s] > best:
+                best, best_s = sprob[s], s
+        out[i] = best_s + 1
+        srt = np.sort(sprob)
+        margin[i] = srt[-1] - srt[-2] if N > 1 else 1.0
+    return out, margin

@@ -255,3 +255,15 @@ def test_align_matches_independent_numpy_transcription(oracle, pkg):
         assert [int(v) for v in r["pass_lm_iters"]] == c["lm_iters"], c["algo"]
         rot, trans = pkg.synth.pose_error(r["pose"], np.array(c["pose7"]))
         assert rot < 1e-7 and trans < 1e-9, (c["algo"], rot, trans)
+
+
+def test_fused_labels_match_independent_numpy_transcription(oracle, pkg):
+    """tests/golden/fused_small.json: getFusedLabels (impl/em_icp.hpp:202-268) from tests/golden/numpy_reference.py.
+    Labels agree wherever the arg-max is not an exact tie (the stored margin between the two best classes)."""
+    with open(os.path.join(GOLD, "fused_small.json")) as f:
+        g = json.load(f)
+    p = pkg.synth.room_pair(seed=g["seed"], n_points=g["n_points"])
+    got = oracle.fused_labels(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["T_gt"])
+    lab, margin = np.array(g["labels"], dtype=np.uint32), np.array(g["margin"])
+    assert np.all((got == lab) | (margin <= 1e-12))
+    assert np.mean(got == lab) > 0.99
