@@ -4,6 +4,7 @@
 // (impl/semantic_icp.hpp:27-166) and EmIterativeClosestPoint::align (impl/em_icp.hpp:24-200).
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,6 +39,15 @@ static sicp_status validate(int algo, const sicp_cloud* src, const sicp_cloud* t
     SICP_REQUIRE(src->has_labels && tgt->has_labels, "EM needs labelled clouds");
   }
   SICP_REQUIRE(o->k_cov >= 1 && o->k_cov <= kMaxK, "k_cov must be in 1..32");
+  return SICP_OK;
+}
+// Sophus::SE3d is a unit quaternion by construction; a pose7 coming through the C ABI has to be checked
+static sicp_status validate_pose(const double* p7, const char* what) {
+  double n2 = 0;
+  bool finite = true;
+  for (int i = 0; i < 7; i++) finite = finite && std::isfinite(p7[i]);
+  for (int i = 0; i < 4; i++) n2 += p7[i] * p7[i];
+  if (!finite || std::fabs(n2 - 1.0) > 1e-6) { set_error(std::string(what) + ": pose7 must be finite with a unit quaternion [qx,qy,qz,qw]"); return SICP_ERR_INVALID; }
   return SICP_OK;
 }
 
@@ -343,6 +353,7 @@ void sicp_options_default(int algo, sicp_options* o) {
 sicp_status sicp_register(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* init7, sicp_result* out) {
   SICP_REQUIRE(init7 && out, "null argument");
   SICP_CHECK(validate(algo, src, tgt, opts));
+  SICP_CHECK(validate_pose(init7, "sicp_register"));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
   std::memset(out, 0, sizeof *out);
@@ -365,6 +376,7 @@ sicp_status sicp_register_batch(int algo, size_t n_pairs, sicp_cloud* const* src
   for (size_t i = 0; i < n_pairs; i++) {
     SICP_CHECK(validate(algo, src[i], tgt[i], opts));
     SICP_REQUIRE(src[i]->device == src[0]->device, "all pairs of a batch must live on one device");
+    SICP_CHECK(validate_pose(init7s + 7 * i, "sicp_register_batch"));
   }
   SICP_CUDA(cudaSetDevice(src[0]->device));
   std::memset(out, 0, sizeof(sicp_result) * n_pairs);

@@ -251,6 +251,10 @@ def test_errors(sicp, room):
     g = sicp.Cloud(room["src_xyz"])
     with pytest.raises(sicp.SicpError):
         g.normals()  # precompute has not run
+    with pytest.raises(sicp.SicpError, match="unit quaternion"):
+        sicp.register(sicp.ALGO_GICP, g, g, sicp.default_options(sicp.ALGO_GICP), np.array([0, 0, 0, 2.0, 0, 0, 0]))
+    with pytest.raises(sicp.SicpError, match="unit quaternion"):
+        sicp.register(sicp.ALGO_GICP, g, g, sicp.default_options(sicp.ALGO_GICP), np.array([0, 0, 0, 1.0, np.nan, 0, 0]))
 
 
 # ------------------------------------------------------------------------------------------------ degenerate inputs
