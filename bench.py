@@ -2,7 +2,7 @@
 """bench.py — scan-pair registrations/sec on KITTI-shaped semantic pairs (BASELINE.json configs[1]).
 
 One "step" = one batch of PAIRS independent EM-ICP registrations (120k-point labelled scan pairs, 20 classes,
-confusion-matrix EM) on one GPU: per pair, cloud construction (Morton sort + box tree) for both scans, k=20
+confusion-matrix EM) on one GPU: per pair, cloud construction (Hilbert sort + box tree) for both scans, k=20
 covariance / label-vector precompute, and every outer pass until the reference's stopping rule
 (reference span: exec/kitti_eval.cc:188-193).
 
@@ -10,10 +10,11 @@ covariance / label-vector precompute, and every outer pass until the reference's
   e2e   : the same through the C ABI with HOST (pinned) buffers: H2D of both clouds and the D2H of the control
           block / result inside the timed region
   --impl reference : the CPU oracle (restatement of the reference; the reference itself cannot be built here) on
-          all host threads, one registration per step.
+          all host threads, one registration per step, cycling through the SAME seeded pairs rank 0 of the GPU arm registers.
 
-Multi-GPU: pairs shard across ranks (weak scaling: PAIRS per rank), no data-path collective; poses are gathered with
-one NCCL all_gather after the timed region.
+Multi-GPU: DISTINCT pairs per rank — global pair i goes to rank i mod N (interleaved shards, weak scaling:
+PAIRS per rank per step), no data-path collective; the 96-byte result records are gathered with all_gathers after
+the timed region (semantic-icp_b200/python/shard.py).
 """
 import argparse
 import json
@@ -23,11 +24,14 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per stream of the batch executor (read when the context is created)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "scan-pair registrations/sec (120k-pt KITTI-shape)"
 ALG_BYTES = {  # algorithmic bytes per unit (N = 20, k_c = 4)
     "cov": 216.0,    # S1 per point (self-kNN(20) + PCA + label vector)
     "knn": 56.0,     # S2 per source point (transform + kNN(4))
@@ -36,15 +40,20 @@ ALG_BYTES = {  # algorithmic bytes per unit (N = 20, k_c = 4)
 }
 
 
+def workload(points):
+    return f"KITTI-shaped pairs, {points} pts/scan, 20 classes, confusion-matrix EM-ICP (configs[1])"
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=16, help="scan pairs per step per GPU")
+    ap.add_argument("--pairs", type=int, default=48, help="scan pairs per step per GPU")
     ap.add_argument("--points", type=int, default=120_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the NYU-shape (configs[2]) line under `extra`")
     return ap.parse_args()
 
 
@@ -91,12 +100,44 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_oracle_run(pair, threads=0):
+def _gen_pair(a):
+    import semantic_icp_b200 as pkg
+
+    return pkg.synth.cached("kitti_pair", a[0], n_points=a[1])
+
+
+def load_pairs(ids, points, procs):
+    """Seeded synthetic pairs (disk-cached; generated on a few host processes the first time)."""
+    import semantic_icp_b200 as pkg
+
+    ids = list(ids)
+    if procs <= 1 or len(ids) <= 2:
+        return [pkg.synth.cached("kitti_pair", i, n_points=points) for i in ids]
+    import multiprocessing as mp
+
+    with mp.get_context("fork").Pool(min(procs, len(ids))) as pool:
+        return pool.map(_gen_pair, [(i, points) for i in ids])
+
+
+def pair_ids(rank, world, B):
+    """Global pair ids of `rank`: interleaved shards of the B * world pairs of one step (shard.shard_ids)."""
+    import semantic_icp_b200 as pkg
+
+    return pkg.shard.shard_ids(B * world, rank, world, "interleaved")
+
+
+def cpu_oracle_run(pair, threads=0, faithful=False):
     from oracle import oracle as O
 
     # every host core this process may use (torchrun exports OMP_NUM_THREADS=1; the baseline must not inherit that)
     threads = threads or len(os.sched_getaffinity(0))
-    r = O.align_em(pair["src_xyz"], pair["src_labels"], pair["tgt_xyz"], pair["tgt_labels"], pair["cm"], pair["init"], threads=threads)
+    # faithful: neighbour-search loops serial and 8 threads in the solve, as the reference runs them (gicp.hpp:66,189; em_icp.hpp:166)
+    O.set_search_threads(1 if faithful else 0)
+    try:
+        r = O.align_em(pair["src_xyz"], pair["src_labels"], pair["tgt_xyz"], pair["tgt_labels"], pair["cm"], pair["init"],
+                       threads=min(8, threads) if faithful else threads)
+    finally:
+        O.set_search_threads(0)
     return r, (threads or O.num_threads())
 
 
@@ -104,25 +145,27 @@ def run_reference(args, rank, world):
     """The reference's CPU path (oracle port: the reference cannot be compiled here), all host threads, rank 0 only."""
     if rank != 0:
         return
-    import semantic_icp_b200 as pkg
-
-    pair = pkg.synth.kitti_pair(0, n_points=args.points)
-    times = []
-    cores = 0
-    for i in range(args.warmup + args.steps):
-        r, cores = cpu_oracle_run(pair)
+    ids = pair_ids(0, world, args.pairs)
+    need = [ids[i % len(ids)] for i in range(args.warmup + args.steps)]
+    uniq = sorted(set(need))
+    pairs = dict(zip(uniq, load_pairs(uniq, args.points, min(8, len(os.sched_getaffinity(0))))))
+    times, cores, passes = [], 0, []
+    for i, pid in enumerate(need):  # step i registers pair ids[i mod B]: the pairs rank 0 of the GPU arm registers in every step
+        r, cores = cpu_oracle_run(pairs[pid])
         if i >= args.warmup:
             times.append(r["seconds"])
+            passes.append(int(r["outer_iter"]))
     total = sum(times)
     v = args.steps / total
     line = {
-        "impl": "reference", "metric": "scan-pair registrations/sec (120k-pt KITTI-shape)", "value": v, "unit": "registrations/s",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "registrations/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"KITTI-shaped pair, {args.points} pts/scan, 20 classes, EM-ICP (configs[1])", "pairs_per_step": 1,
-                   "algo": "EmIterativeClosestPoint<20>"},
+        "config": {"workload": workload(args.points), "pairs_per_step": 1, "algo": "EmIterativeClosestPoint<20>", "k_cov": 20, "k_corr": 4,
+                   "pair_ids": need[args.warmup:], "outer_passes": passes},
         "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": cores, "kind": "port",
-                         "sample": "one full 120k-point EM-ICP registration per step (oracle restatement, OpenMP all threads)"},
+                         "sample": "one full 120k-point EM-ICP registration per step, cycling through the pairs of the GPU arm's rank 0 "
+                                   "(oracle restatement, OpenMP on all host threads)"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -144,16 +187,16 @@ def main():
     sicp, synth = pkg.sicp, pkg.synth
     if not torch.cuda.is_available() or sicp.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    B, n = args.pairs, args.points
+    ids = pair_ids(rank, world, B)  # DISTINCT pairs on every rank
+    # generated (or read from the disk cache) before this process touches CUDA: the generator pool forks
+    pairs = load_pairs(ids, n, max(1, min(8, len(os.sched_getaffinity(0)) // max(1, world))))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B, n = args.pairs, args.points
-    # every rank registers the SAME B seeded pairs: weak scaling with identical per-GPU work (distinct shards make the
-    # max-over-ranks time a measure of shard-to-shard data variance: 39-47 ms/step across 4 ranks)
-    pairs = [synth.kitti_pair(i, n_points=n) for i in range(B)]
     cm = pairs[0]["cm"]
     opts = sicp.default_options(sicp.ALGO_EM, cm=cm)
     inits = np.stack([p["init"] for p in pairs])
@@ -172,51 +215,60 @@ def main():
     torch.cuda.synchronize()
     sicp.set_stream(None)  # legacy default stream == torch's current stream here, so torch events bracket our work
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # clouds are built on a few side streams (sicp_set_stream) so that the sorts / tree builds of different pairs overlap;
+    # the batch executor waits for each cloud's build event, and joins its slots back into the default stream at the end
+    build_streams = [torch.cuda.Stream(device=dev) for _ in range(8)]
 
-    def step_device():
+    def make_clouds(make):
+        gate = torch.cuda.Event()
+        gate.record()  # side streams start after everything already on the default stream (L2 flush, start event)
+        for s in build_streams:
+            s.wait_event(gate)
         cl = []
-        for (sx, sl, tx, tl) in d_in:
-            s = sicp.Cloud.from_device(sx.data_ptr(), sl.data_ptr(), n, device=local_rank)
-            t = sicp.Cloud.from_device(tx.data_ptr(), tl.data_ptr(), n, device=local_rank)
-            cl.append((s, t))
+        for i in range(B):
+            sicp.set_stream(build_streams[i % len(build_streams)].cuda_stream)
+            cl.append(make(i))
+        sicp.set_stream(None)
+        return cl
+
+    def step(make):
+        cl = make_clouds(make)
         res = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], opts, inits)
         for s, t in cl:
             s.close(); t.close()
         return res
 
-    def step_host():
-        cl = []
-        for (sx, sl, tx, tl) in h_in:
-            s = sicp.Cloud(sx.numpy(), sl.numpy().view(np.uint32), device=local_rank)
-            t = sicp.Cloud(tx.numpy(), tl.numpy().view(np.uint32), device=local_rank)
-            cl.append((s, t))
-        res = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], opts, inits)
-        for s, t in cl:
-            s.close(); t.close()
-        return res
+    def make_device(i):
+        sx, sl, tx, tl = d_in[i]
+        return (sicp.Cloud.from_device(sx.data_ptr(), sl.data_ptr(), n, device=local_rank),
+                sicp.Cloud.from_device(tx.data_ptr(), tl.data_ptr(), n, device=local_rank))
+
+    def make_host(i):
+        sx, sl, tx, tl = h_in[i]
+        return (sicp.Cloud(sx.numpy(), sl.numpy().view(np.uint32), device=local_rank),
+                sicp.Cloud(tx.numpy(), tl.numpy().view(np.uint32), device=local_rank))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, sampler=None):
+    def timed(make, steps, warmup, sampler=None):
         for _ in range(warmup):
-            step_fn()
+            step(make)
         barrier()
         if sampler:
             sampler.start()
-        total_ms, wall0, res = 0.0, time.perf_counter(), None
+        total_ms, res = 0.0, None
         for _ in range(steps):
             flush_buf.zero_()  # flush L2 between timed iterations (outside the events)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            res = step_fn()
+            res = step(make)
             e1.record()
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
         barrier()
-        wall = time.perf_counter() - wall0
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         by_rank = [total_ms]
         if world > 1:
@@ -225,20 +277,20 @@ def main():
             by_rank = [float(x.item()) for x in allt]
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         timed.by_rank = by_rank
-        return float(t.item()), res, wall
+        return float(t.item()), res
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
-        step_device()
+        step(make_device)
     l0 = sicp.launch_count()
-    ms_dev, res_dev, _ = timed(step_device, args.steps, 0, sampler)
+    ms_dev, res_dev = timed(make_device, args.steps, 0, sampler)
     ms_dev_by_rank = [round(x / args.steps, 3) for x in timed.by_rank]
     launches = sicp.launch_count() - l0
     clocks = sampler.summary() if sampler else None
-    ms_e2e, res_e2e, _ = timed(step_host, args.steps, max(1, args.warmup // 2))
+    ms_e2e, res_e2e = timed(make_host, args.steps, max(1, args.warmup // 2))
 
-    # result gather: the only collective on this path — one all_gather of 96-byte records, after the timed region
-    records = pkg.shard.gather_records(pkg.shard.to_records(res_dev), [B] * world, device=dev)
+    # result gather: the only collectives on this path, after the timed region — 96-byte records in global pair order
+    records = pkg.shard.gather_by_id(ids, pkg.shard.to_records(res_dev), B * world, device=dev)
 
     if rank == 0:
         total_pairs = B * world
@@ -272,7 +324,7 @@ def main():
         except Exception:
             pass
         launches_per_unit = {"cov": 2, "knn": prof["outer_iter"], "estep": prof["outer_iter"], "lm": prof["outer_iter"]}
-        roofline = {"kernel": {"cov": "self_knn_pca_kernel<20>", "knn": "cross_knn_kernel<4>", "estep": "estep_kernel", "lm": "lm_kernel"}[dom],
+        roofline = {"kernel": {"cov": "self_knn_pca_kernel<20>", "knn": "cross_knn_kernel<4>", "estep": "estep_kernel<4>", "lm": "lm_kernel"}[dom],
                     "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
                     "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": round(kernels[dom]["ms_total"] / max(1, launches_per_unit[dom]), 4),
@@ -300,40 +352,77 @@ def main():
             e1.synchronize()
             knn_qps[f"k{k}"] = n * reps / (e0.elapsed_time(e1) * 1e-3)
         s.close(); t.close()
+        extra = {}
+        if not args.no_extra and n == 120_000:
+            # configs[2]: NYU-depth-shaped pairs (640x480 back-projected depth, 307,200 points, 40 classes), EM-ICP
+            try:
+                nyu = [synth.cached("nyu_pair", i) for i in range(4)]
+                nopts = sicp.default_options(sicp.ALGO_EM, cm=nyu[0]["cm"])
+                ninit = np.stack([q["init"] for q in nyu])
+
+                def nyu_step():
+                    cl = [(sicp.Cloud(q["src_xyz"], q["src_labels"], device=local_rank), sicp.Cloud(q["tgt_xyz"], q["tgt_labels"], device=local_rank)) for q in nyu]
+                    r = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], nopts, ninit)
+                    for a, b in cl:
+                        a.close(); b.close()
+                    return r
+
+                nyu_step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                reps = 3
+                for _ in range(reps):
+                    nres = nyu_step()
+                e1.record()
+                e1.synchronize()
+                extra["nyu_shape"] = {"workload": "NYU-depth-shaped pairs, 307200 pts/scan, 40 classes, EM-ICP (configs[2]), host buffers through the C ABI",
+                                      "value": len(nyu) * reps / (e0.elapsed_time(e1) * 1e-3), "unit": "registrations/s", "pairs_per_step": len(nyu),
+                                      "outer_passes": [r["outer_iter"] for r in nres], "lm_iters": [r["lm_iters_total"] for r in nres]}
+            except Exception as ex:  # the headline line must not depend on the extra workload
+                extra["nyu_shape"] = {"error": repr(ex)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N=1 only
             r, cores = cpu_oracle_run(p0)
+            rf, _ = cpu_oracle_run(p0, faithful=True)
             from oracle import oracle as O
 
             q = O.transform_points(p0["T_gt"], p0["src_xyz"])
             cpu_knn = {}
-            q4 = np.tile(q, (4, 1))
-            for k in (1, 4, 20):  # the oracle's exact kd-tree search on all host threads; the tree build cancels in the difference
-                t0 = time.perf_counter()
-                O.knn(p0["tgt_xyz"], q, k, threads=cores)
-                t1 = time.perf_counter() - t0
-                t0 = time.perf_counter()
-                O.knn(p0["tgt_xyz"], q4, k, threads=cores)
-                cpu_knn[f"k{k}"] = 3 * n / max(1e-9, time.perf_counter() - t0 - t1)
+            for k in (1, 4, 20):  # the oracle's exact kd-tree search on all host threads; best of 3, tree build excluded by the 1-query run
+                best = 1e9
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    O.knn(p0["tgt_xyz"], q[:1], k, threads=cores)
+                    tb = time.perf_counter() - t0
+                    t0 = time.perf_counter()
+                    O.knn(p0["tgt_xyz"], q, k, threads=cores)
+                    best = min(best, max(1e-9, time.perf_counter() - t0 - tb))
+                cpu_knn[f"k{k}"] = n / best
             cpu = {"value": 1.0 / r["seconds"], "unit": "registrations/s", "cores": cores, "kind": "port", "knn_queries_per_s": cpu_knn,
-                   "sample": "one full 120k-point EM-ICP registration of pair 0 (oracle restatement, OpenMP all threads)",
-                   "seconds": r["seconds"], "pose_diff_vs_gpu": list(synth.pose_error(r["pose"], res_dev[0]["pose"]))}
+                   "sample": f"one full 120k-point EM-ICP registration of pair {ids[0]} (oracle restatement, OpenMP all threads)",
+                   "seconds": r["seconds"], "pose_diff_vs_gpu": list(synth.pose_error(r["pose"], res_dev[0]["pose"])),
+                   "reference_threading": {"value": 1.0 / rf["seconds"], "seconds": rf["seconds"], "search_threads": 1, "solve_threads": min(8, cores),
+                                           "note": "neighbour searches and covariances serial, residual evaluation on 8 threads, as the reference "
+                                                   "runs them (impl/gicp.hpp:66,189; impl/em_icp.hpp:57,166,288)"}}
         h2d = sum(int(t.numel() * t.element_size()) for hp in h_in for t in hp)
         d2h = sum(r["d2h_bytes"] for r in res_e2e)
+        passes = records[:, 7].astype(int)
         line = {
-            "metric": "scan-pair registrations/sec (120k-pt KITTI-shape)", "value": value, "unit": "registrations/s", "n_gpus": world,
+            "metric": METRIC, "value": value, "unit": "registrations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"KITTI-shaped pairs, {n} pts/scan, 20 classes, confusion-matrix EM-ICP (configs[1])",
-                       "pairs_per_step_per_gpu": B, "shards": "every rank registers the same seeded pairs (identical per-GPU work)",
+            "config": {"workload": workload(n),
+                       "pairs_per_step_per_gpu": B, "shards": "distinct pairs per rank: global pair i -> rank i mod N (interleaved), B*N pairs per step",
                        "algo": "EmIterativeClosestPoint<20>", "k_cov": 20, "k_corr": 4,
                        "l2": "flushed between timed steps (256 MiB memset outside the events); per-step working set > L2",
-                       "outer_passes": [r["outer_iter"] for r in res_dev], "lm_iters": [r["lm_iters_total"] for r in res_dev]},
+                       "outer_passes_hist": {int(k): int(v) for k, v in zip(*np.unique(passes, return_counts=True))},
+                       "lm_iters_mean": float(records[:, 8].mean())},
             "e2e": {"value": e2e_v, "unit": "registrations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "ms_per_step_by_rank": ms_dev_by_rank, "records_gathered": int(records.shape[0]), "knn_queries_per_s": knn_qps,
+            "ms_per_step_by_rank": ms_dev_by_rank, "records_gathered": int(records.shape[0]), "knn_queries_per_s": knn_qps, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

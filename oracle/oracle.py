@@ -60,6 +60,12 @@ def _u32(a):
     return np.ascontiguousarray(a, dtype=np.uint32)
 
 
+def set_search_threads(t):
+    """Threads of the neighbour-search loops: 0 = same as the `threads` argument of each call (all-cores baseline),
+    1 = serial like the reference (gicp.hpp:66,189; em_icp.hpp:57,288)."""
+    lib().orc_set_search_threads(C.c_int(int(t)))
+
+
 def num_threads():
     return int(lib().orc_num_threads())
 

@@ -460,11 +460,18 @@ static inline void transform_point(const M3& R, const double* t, const float* p,
 
 // ------------------------------------------------------------------ covariances (gicp.hpp:177-239; em_icp.hpp:270-344;
 //                                                                     semantic_point_cloud.hpp:25-84)
+// Threading of the neighbour-search loops (kNN queries, covariances, correspondence search).  The reference runs them
+// SERIALLY (plain for loops: gicp.hpp:66,189; em_icp.hpp:57,288; semantic_icp.hpp:62) and only the Ceres residual
+// evaluation on 8 (4 for SemanticICP) threads (gicp.hpp:142, em_icp.hpp:166, semantic_icp.hpp:140).  0 = use the `threads`
+// argument for these loops too ("all cores" baseline); 1 = reference-faithful.  Results do not depend on it.
+static int g_search_threads = 0;
+static inline int search_threads(int threads) { return g_search_threads > 0 ? g_search_threads : threads; }
+
 static void covariances(const float* xyz, const uint32_t* labels, int n, const KdTree& tree, int k, double eps,
                         int N, double* cov_out /*n*9*/, double* dist_out /*n*N or null*/, double* normal_out /*n*3 or null*/,
                         int32_t* nn_out /*n*k or null*/, int threads) {
   const double increment = 1.0 / static_cast<double>(k);
-#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(search_threads(threads))
   for (int it = 0; it < n; it++) {
     std::vector<Cand> buf(k);
     int nn = 0;
@@ -789,6 +796,8 @@ struct orc_trace {      // optional per-pass trace (arrays sized by caller: max_
 };
 struct orc_result { double pose7[7]; int outer_iter; int lm_iters_total; double final_cost; int n_corr_last; double seconds; };
 
+void orc_set_search_threads(int t) { g_search_threads = t; }
+
 int orc_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();
@@ -905,7 +914,7 @@ void orc_align_gicp(const float* sxyz, int ns, const float* txyz, int nt, int k,
     SE3 est = cur;
     M3 R = quat_to_R(cur.q);
     for (int i = 0; i < ns; i++) transform_point(R, cur.t, sxyz + 3 * (size_t)i, &tsrc[3 * (size_t)i]);
-#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(search_threads(threads))
     for (int i = 0; i < ns; i++) { Cand c; int m = 0; ttree.knn(&tsrc[3 * (size_t)i], 1, &c, &m); nn[i] = m ? c.i : -1; nd[i] = m ? c.d : INFINITY; }
     Problem P{sxyz, scov.data(), txyz, tcov.data(), {}, LOSS_GICP};
     for (int i = 0; i < ns; i++) if (nn[i] >= 0 && nd[i] < 250) P.res.push_back(Residual{i, nn[i], 1.0});
@@ -942,7 +951,7 @@ void orc_align_em(const float* sxyz, const uint32_t* slab, int ns, const float* 
     M3 R = quat_to_R(cur.q);
     for (int i = 0; i < ns; i++) transform_point(R, cur.t, sxyz + 3 * (size_t)i, &tsrc[3 * (size_t)i]);
     Problem P{sxyz, scov.data(), txyz, tcov.data(), {}, LOSS_EM};
-#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(search_threads(threads))
     for (int i = 0; i < ns; i++) {
       Cand c[KC]; int m = 0; ttree.knn(&tsrc[3 * (size_t)i], KC, c, &m);
       for (int j = 0; j < KC; j++) {
@@ -992,7 +1001,7 @@ void orc_fused_labels(const float* sxyz, const uint32_t* slab, int ns, const flo
   SE3 T = se3_from7(pose7);
   M3 R = quat_to_R(T.q);
   Problem P{sxyz, scov.data(), txyz, tcov.data(), {}, LOSS_EM};
-#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(search_threads(threads))
   for (int i = 0; i < ns; i++) {
     float q[3]; transform_point(R, T.t, sxyz + 3 * (size_t)i, q);
     Cand c[4]; int m = 0; ttree.knn(q, 4, c, &m);
@@ -1067,7 +1076,7 @@ void orc_align_semantic(const float* sxyz, const uint32_t* slab, int ns, const f
       int m = (int)sc.orig.size();
       if (!(m > 400)) continue;                                    // :51
       std::vector<int32_t> nn(m); std::vector<float> nd(m);
-#pragma omp parallel for schedule(dynamic, 256) num_threads(threads)
+#pragma omp parallel for schedule(dynamic, 256) num_threads(search_threads(threads))
       for (int i = 0; i < m; i++) {
         float q[3]; transform_point(R, cur.t, &sc.xyz[3 * (size_t)i], q);
         Cand c; int got = 0; tc.tree.knn(q, 1, &c, &got);

@@ -124,7 +124,7 @@ __global__ void slot_kernel(const float* __restrict__ xyz, const uint32_t* __res
 // level 0: one warp per leaf
 __global__ void leaf_box_kernel(const float4* __restrict__ pts, const int* __restrict__ seg_of_leaf, const Segment* __restrict__ seg,
                                 int nleaf, const int* __restrict__ bb, float4* node_lo, float4* node_hi, uint32_t* leaf_key) {
-  const int leaf = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int leaf = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) / 32);
   if (leaf >= nleaf) return;
   const float4 p = pts[(size_t)leaf * kLeaf + (threadIdx.x & 31)];
   float lo[3] = {p.x, p.y, p.z}, hi[3] = {p.x, p.y, p.z};
@@ -246,7 +246,7 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
   else seg_of_leaf_kernel<<<(c->nleaf + T - 1) / T, T, 0, st>>>(c->d_seg, nseg, c->nleaf, c->d_seg_of_leaf);
   slot_kernel<<<(c->nslots + T - 1) / T, T, 0, st>>>(d_xyz, d_labels, vals2, c->d_seg_of_leaf, c->d_seg, c->nslots, c->d_pts, c->d_label,
                                                      c->d_slot_of_orig);
-  leaf_box_kernel<<<(c->nleaf * 32 + T - 1) / T, T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_bb, c->d_node_lo, c->d_node_hi, c->d_leaf_key);
+  leaf_box_kernel<<<(unsigned)(((size_t)c->nleaf * 32 + T - 1) / T), T, 0, st>>>(c->d_pts, c->d_seg_of_leaf, c->d_seg, c->nleaf, c->d_bb, c->d_node_lo, c->d_node_hi, c->d_leaf_key);
   upper_box_kernel<<<nseg, 256, 0, st>>>(c->d_seg, c->d_node_lo, c->d_node_hi);
   count_launches(6 + (nseg > 1) + ((wide ? 39 : 30) + 7) / 8 + 2);  // own kernels + CUB onesweep (histogram, scan, one pass per 8 key bits)
   SICP_CUDA(cudaGetLastError());
@@ -414,7 +414,7 @@ sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* la
   SICP_REQUIRE(out, "out is null");
   SICP_REQUIRE(xyz || n == 0, "xyz is null");
   SICP_REQUIRE(xyz_stride >= 12 && (labels == nullptr || label_stride >= 4), "stride too small");
-  SICP_REQUIRE(n < (1u << 30), "too many points");
+  SICP_REQUIRE(n <= kMaxCloudPoints, "too many points (at most 2^26 per cloud)");
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || layout == SICP_CLOUD_PER_CLASS, "bad layout");
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || labels, "PER_CLASS layout needs labels");
   SICP_CHECK(init_device(device));
@@ -441,7 +441,7 @@ sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* la
 sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_labels, size_t n, int layout, int device, sicp_cloud** out) {
   SICP_REQUIRE(out, "out is null");
   SICP_REQUIRE(d_xyz || n == 0, "d_xyz is null");
-  SICP_REQUIRE(n < (1u << 30), "too many points");
+  SICP_REQUIRE(n <= kMaxCloudPoints, "too many points (at most 2^26 per cloud)");
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || layout == SICP_CLOUD_PER_CLASS, "bad layout");
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || d_labels, "PER_CLASS layout needs labels");
   SICP_CHECK(init_device(device));
@@ -481,9 +481,11 @@ sicp_status sicp_cloud_transform_f32(const sicp_cloud* c, const double* pose7, v
   // Matrix4f path of the finalisation (gicp.hpp:166-171, em_icp.hpp:192-197, semantic_point_cloud.hpp:105-111): the pose
   // is cast to a float 4x4 and applied in float arithmetic, on the device, to the points in the caller's original order.
   SICP_REQUIRE(c && pose7 && out_xyz && out_stride >= 12, "bad argument");
+  SICP_CHECK(validate_pose7(pose7, "sicp_cloud_transform_f32"));
   cudaStream_t st = current_stream();
   SICP_CUDA(cudaSetDevice(c->device));
   if (c->n == 0) return SICP_OK;
+  SICP_CUDA(c->wait_built(st));
   double Rd[9];
   quat_to_R(pose7, Rd);
   Mat34f M;

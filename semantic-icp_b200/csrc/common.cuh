@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "sicp_b200.h"
@@ -34,6 +35,9 @@ void set_error(const std::string& msg);
 
 cudaStream_t current_stream();
 void count_launches(int n);  // per-thread kernel launch counter (sicp_launch_count)
+// Sophus::SE3d is a unit quaternion by construction; a pose7 that comes through the C ABI has to be checked
+// (finite, |q| = 1) before it reaches quat_to_R.  nullable: a null pointer is accepted (optional pose arguments).
+sicp_status validate_pose7(const double* p7, const char* what, bool nullable = false);
 
 // pinned staging blocks for small host->device tables (see cloud.cu)
 struct PinnedBlock { void* p; size_t bytes; cudaEvent_t ev; };
@@ -46,6 +50,7 @@ constexpr int kArity = 8;        // children per internal node
 constexpr int kMaxLevels = 10;   // 32 * 8^9 points
 constexpr int kMaxClasses = 64;  // label vectors live in registers of two lanes-worth (N <= 64)
 constexpr int kMaxK = 32;
+constexpr size_t kMaxCloudPoints = (size_t)1 << 26;  // 32-bit launch / index arithmetic of the per-slot kernels holds up to here (x32 lanes, x4 candidates)
 
 // One searchable point set: the whole cloud, or one semantic class (SemanticPointCloud::labeledKdTrees).
 struct Segment {
@@ -110,5 +115,14 @@ struct sicp_cloud {
   bool label_range_known = false;
   cudaEvent_t ready_ev = nullptr;  // recorded after the last precompute; consumers on other streams wait on it
   cudaEvent_t built_ev = nullptr;  // recorded after the build (upload, sort, tree); work on other streams waits on it
+  std::mutex mu;                   // guards the precompute cache (pairs of an odometry chain share clouds across host threads)
   sicp::CloudView view() const;
+  // Every entry point that reads the cloud on stream `st` calls these first (a wait on a completed event costs nothing):
+  // the cloud may have been built / precomputed on another stream or by another host thread.
+  cudaError_t wait_built(cudaStream_t st) const { return built_ev ? cudaStreamWaitEvent(st, built_ev, 0) : cudaSuccess; }
+  cudaError_t wait_ready(cudaStream_t st) const {
+    cudaError_t e = wait_built(st);
+    if (e == cudaSuccess && ready_ev) e = cudaStreamWaitEvent(st, ready_ev, 0);
+    return e;
+  }
 };

@@ -31,7 +31,12 @@ struct LMConfig {
   int max_iter;          // 400
   double mse_stop;       // 1e-5 (GICP, EM) / 1e-3 (SEMANTIC)
   int outer_cap;         // 50 / 35
+  int variant;           // shape of the LM kernel (lm.cu: kLmShapes)
 };
+constexpr int kLmVariants = 5;
+constexpr int kLmMaxGrid = 320;       // block partials reserved per workspace
+constexpr int kLmSyncDoubles = 32;    // LMSync lives in front of the partials
+constexpr size_t kLmPartialsDoubles = kLmSyncDoubles + (size_t)kLmMaxGrid * 28;
 
 sicp_status launch_self_knn_pca(const sicp_cloud* c, int k, double* d_nrm, int* d_selfnn, uint8_t* d_nbr_label, cudaStream_t st);
 sicp_status launch_cross_knn(const sicp_cloud* src, const sicp_cloud* tgt, const double* d_pose7, const int* d_stop, const int* d_tseg_of_sseg,
@@ -44,8 +49,11 @@ sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMC
                          cudaStream_t st);
 // M-step: one inner solve (ceres::Solve at impl/gicp.hpp:149-151) + outer-loop bookkeeping, cooperative kernel
 int lm_grid_blocks(int device);
+int lm_max_grid(int device, int algo, int variant);
+// cond_handle != 0: the launch is being captured as the last node of a graph WHILE body; the kernel sets the handle to
+// "not converged" so that the graph runs another pass without the host
 sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt, RegCtl* d_ctl,
-                      double* d_partials, int grid, cudaStream_t st);
+                      double* d_partials, int grid, cudaStream_t st, unsigned long long cond_handle = 0);
 // Single evaluation (cost, g, H) at a given pose, for parity tests
 sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt,
                             const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st);

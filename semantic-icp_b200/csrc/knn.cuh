@@ -35,7 +35,15 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
   v = (v | (v << 2)) & 0x09249249;
   return v;
 }
-// 30-bit Morton code (10 bits per axis) of (x,y,z) in the bounding cube described by bb (ordered ints, see bbox_kernel)
+#ifndef SICP_CURVE_HILBERT
+#define SICP_CURVE_HILBERT 1
+#endif
+// 30-bit space-filling-curve key (10 bits per axis) of (x,y,z) in the bounding cube described by bb (ordered ints, see
+// bbox_kernel).  The key only decides the ORDER of the points (which 32 of them share a leaf) and the home-leaf lookup;
+// search results do not depend on it.  Hilbert order (Skilling's transpose algorithm): consecutive keys are always
+// adjacent cells, so a run of 32 points never straddles one of the long jumps of the Z-order curve — on KITTI-shaped
+// scans the leaf boxes a query ball meets drop from 5.8 to 4.0 (k = 4) and the leaves a 32-query packet scans from
+// 13.7 to 9.4 (tools/sim_knn.py).  SICP_CURVE_HILBERT=0 builds the Z-order (Morton) variant for A/B runs.
 __device__ __forceinline__ uint32_t morton30(float x, float y, float z, const int* __restrict__ bb) {
   float lo[3], ext = 0.f;
 #pragma unroll
@@ -43,13 +51,28 @@ __device__ __forceinline__ uint32_t morton30(float x, float y, float z, const in
   if (!(ext > 0.f) || !isfinite(ext)) ext = 1.f;
   const float inv_cell = 1023.f / ext;
   const float p[3] = {x, y, z};
-  uint32_t m = 0;
+  uint32_t X[3];
 #pragma unroll
-  for (int c = 0; c < 3; c++) {
-    const float f = fminf(fmaxf((p[c] - lo[c]) * inv_cell, 0.f), 1023.f);
-    m |= spread10((uint32_t)f) << c;
+  for (int c = 0; c < 3; c++) X[c] = (uint32_t)fminf(fmaxf((p[c] - lo[c]) * inv_cell, 0.f), 1023.f);
+#if SICP_CURVE_HILBERT
+#pragma unroll
+  for (uint32_t Q = 512; Q > 1; Q >>= 1) {  // inverse undo
+    const uint32_t P = Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (X[i] & Q) X[0] ^= P;
+      else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+    }
   }
-  return m;
+  X[1] ^= X[0]; X[2] ^= X[1];  // Gray encode
+  uint32_t t = 0;
+#pragma unroll
+  for (uint32_t Q = 512; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+  X[0] ^= t; X[1] ^= t; X[2] ^= t;
+  return (spread10(X[0]) << 2) | (spread10(X[1]) << 1) | spread10(X[2]);
+#else
+  return spread10(X[0]) | (spread10(X[1]) << 1) | (spread10(X[2]) << 2);
+#endif
 }
 
 #ifdef SICP_STATS

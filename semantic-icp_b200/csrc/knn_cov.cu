@@ -176,27 +176,34 @@ __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, co
 
 // ------------------------------------------------------------------ K1b: label distribution -> a_p = CM^T dist_p
 // one warp per point; dist[b] is the repeated f64 sum of 1/k (em_icp.hpp:279,301), a[s] = sum_b dist[b]*CM[b][s].
+// Lane j holds the label of neighbour j.  Only the DISTINCT labels among the k neighbours (typically 1-3 of N) are
+// visited, in ascending label order — the same sequence of non-zero terms as the reference's loop over b = 0..N-1 —
+// each found with one warp-wide min-reduction.  dist_out (parity tests) must be zeroed by the caller.
 __global__ void label_vector_kernel(CloudView cv, int k, int N, const double* __restrict__ cm, const uint8_t* __restrict__ nbr_label,
                                     double* __restrict__ avec, double* __restrict__ dist_out) {
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long slot = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (slot >= cv.nslots) return;
-  const bool valid = __float_as_int(cv.pts[slot].w) >= 0;
-  const int lab = (lane < k) ? nbr_label[(size_t)slot * kMaxK + lane] : 0;
+  const bool valid = __float_as_int(cv.pts[slot].w) >= 0;  // padding slots carry no neighbour labels
+  unsigned lab = (valid && lane < k) ? nbr_label[(size_t)slot * kMaxK + lane] : 0u;
+  if (lab > (unsigned)N) lab = 0u;  // labels were range-checked on the host; keeps the CM row index in bounds regardless
   const double inc = 1.0 / (double)k;
   double a0 = 0, a1 = 0;
-  for (int b = 0; b < N; b++) {
-    const int cnt = __popc(__ballot_sync(kFull, lab == b + 1));
+  unsigned remaining = __ballot_sync(kFull, lab != 0u);
+  while (remaining) {
+    const unsigned b = __reduce_min_sync(kFull, ((remaining >> lane) & 1u) ? lab : 0xffffffffu);  // smallest label not yet visited
+    const unsigned grp = __ballot_sync(kFull, lab == b);
+    const int cnt = __popc(grp);
     double d = 0;
     for (int i = 0; i < cnt; i++) d += inc;
-    if (dist_out && lane == 0 && valid) dist_out[(size_t)slot * N + b] = d;
-    if (cnt) {
-      if (lane < N) a0 += d * cm[b * N + lane];
-      if (lane + 32 < N) a1 += d * cm[b * N + lane + 32];
-    }
+    if (dist_out && lane == 0) dist_out[(size_t)slot * N + (b - 1)] = d;
+    const double* row = cm + (size_t)(b - 1) * N;
+    if (lane < N) a0 += d * __ldg(&row[lane]);
+    if (lane + 32 < N) a1 += d * __ldg(&row[lane + 32]);
+    remaining &= ~grp;
   }
-  if (lane < N) avec[(size_t)slot * N + lane] = valid ? a0 : 0.0;
-  if (lane + 32 < N) avec[(size_t)slot * N + lane + 32] = valid ? a1 : 0.0;
+  if (lane < N) avec[(size_t)slot * N + lane] = a0;
+  if (lane + 32 < N) avec[(size_t)slot * N + lane + 32] = a1;
 }
 
 // ------------------------------------------------------------------ K2: transform + cross kNN
@@ -377,11 +384,20 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
   SICP_REQUIRE(N >= 0 && N <= kMaxClasses, "n_classes must be in 0..64");
   SICP_REQUIRE(N == 0 || cm, "confusion matrix is null");
   SICP_REQUIRE(N == 0 || c->has_labels, "EM precompute needs a labelled cloud");
+  // The cache check, the buffers and the ready event are guarded by the cloud's mutex: pairs of an odometry chain share
+  // clouds, possibly across host threads.
+  std::lock_guard<std::mutex> lock(c->mu);
   if (c->pre_valid && c->pre_k == k_cov && c->pre_eps == eps && c->pre_N == N &&
       (N == 0 || std::memcmp(c->pre_cm.data(), cm, sizeof(double) * N * N) == 0))
     return SICP_OK;
   cudaStream_t st = current_stream();
   SICP_CUDA(cudaSetDevice(c->device));
+  SICP_CUDA(c->wait_built(st));
+  if (c->d_nrm || c->d_avec) {
+    // Re-precompute with other parameters (rare): registrations on other streams may still be reading the old normals /
+    // label vectors, so drain the device before they are overwritten or freed.
+    SICP_CUDA(cudaDeviceSynchronize());
+  }
   c->pre_valid = false;
   if (!c->d_nrm) SICP_CUDA(cudaMallocAsync(&c->d_nrm, sizeof(double) * 3 * std::max(1, c->nslots), st));
   if (c->d_avec) { SICP_CUDA(cudaFreeAsync(c->d_avec, st)); c->d_avec = nullptr; }
@@ -412,7 +428,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
     c->pre_cm.assign(cm, cm + N * N);
     if (c->nslots) {
       CloudView cv = c->view();
-      label_vector_kernel<<<(c->nslots * 32 + 255) / 256, 256, 0, st>>>(cv, k_cov, N, d_cm, d_nbr, c->d_avec, nullptr);
+      label_vector_kernel<<<(unsigned)(((size_t)c->nslots * 32 + 255) / 256), 256, 0, st>>>(cv, k_cov, N, d_cm, d_nbr, c->d_avec, nullptr);
       count_launches(1);
       SICP_CUDA(cudaGetLastError());
     }
@@ -427,6 +443,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
 
 static sicp_status download_rows(const sicp_cloud* c, const double* d_in, int cols, int soa, double* out) {
   cudaStream_t st = current_stream();
+  SICP_CUDA(c->wait_ready(st));
   double* d_tmp;
   SICP_CUDA(cudaMallocAsync(&d_tmp, sizeof(double) * cols * std::max<size_t>(1, c->n), st));
   if (c->nslots) unsort_rows_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->view(), d_in, cols, soa, d_tmp);
@@ -447,6 +464,7 @@ sicp_status sicp_cloud_get_covariances(const sicp_cloud* c, double* out) {
   if (!c->pre_valid) { set_error("precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = current_stream();
+  SICP_CUDA(c->wait_ready(st));
   double* d_tmp;
   SICP_CUDA(cudaMallocAsync(&d_tmp, sizeof(double) * 9 * std::max<size_t>(1, c->n), st));
   if (c->nslots) cov_rows_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->view(), c->pre_eps, d_tmp);
@@ -467,6 +485,7 @@ sicp_status sicp_cloud_get_label_distributions(const sicp_cloud* c, double* out)
   if (!c->pre_valid || c->pre_N == 0) { set_error("EM precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = current_stream();
+  SICP_CUDA(c->wait_ready(st));
   const int N = c->pre_N;
   uint8_t* d_nbr; double *d_cm, *d_dist, *d_a, *d_n;
   SICP_CUDA(cudaMallocAsync(&d_nbr, (size_t)kMaxK * std::max(1, c->nslots), st));
@@ -477,7 +496,7 @@ sicp_status sicp_cloud_get_label_distributions(const sicp_cloud* c, double* out)
   SICP_CUDA(cudaMemcpyAsync(d_cm, c->pre_cm.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
   SICP_CUDA(cudaMemsetAsync(d_dist, 0, sizeof(double) * N * std::max(1, c->nslots), st));
   SICP_CHECK(launch_self_knn_pca(c, c->pre_k, d_n, nullptr, d_nbr, st));
-  if (c->nslots) label_vector_kernel<<<(c->nslots * 32 + 255) / 256, 256, 0, st>>>(c->view(), c->pre_k, N, d_cm, d_nbr, d_a, d_dist);
+  if (c->nslots) label_vector_kernel<<<(unsigned)(((size_t)c->nslots * 32 + 255) / 256), 256, 0, st>>>(c->view(), c->pre_k, N, d_cm, d_nbr, d_a, d_dist);
   sicp_status rc = download_rows(c, d_dist, N, 0, out);
   cudaFreeAsync(d_nbr, st); cudaFreeAsync(d_cm, st); cudaFreeAsync(d_dist, st); cudaFreeAsync(d_a, st); cudaFreeAsync(d_n, st);
   return rc;
@@ -487,6 +506,7 @@ sicp_status sicp_cloud_get_self_neighbours(const sicp_cloud* c, int32_t* out) {
   if (!c->pre_valid) { set_error("precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = current_stream();
+  SICP_CUDA(c->wait_ready(st));
   const int k = c->pre_k;
   int* d_nn; int32_t* d_out; double* d_n;
   SICP_CUDA(cudaMallocAsync(&d_nn, sizeof(int) * k * std::max(1, c->nslots), st));
@@ -504,8 +524,11 @@ sicp_status sicp_knn_cloud(const sicp_cloud* tgt, const sicp_cloud* q, const dou
   SICP_REQUIRE(tgt && q && d_idx_out && d_d2_out, "null argument");
   SICP_REQUIRE(k >= 1 && k <= kMaxK, "k must be in 1..32");
   SICP_REQUIRE(tgt->device == q->device, "clouds live on different devices");
+  SICP_CHECK(validate_pose7(pose7, "sicp_knn_cloud", true));
   SICP_CUDA(cudaSetDevice(tgt->device));
   cudaStream_t st = current_stream();
+  SICP_CUDA(tgt->wait_built(st));
+  SICP_CUDA(q->wait_built(st));
   int* d_map = nullptr;
   SICP_CHECK(make_class_map(q, tgt, -1, &d_map, st));
   double* d_pose = nullptr;
@@ -535,6 +558,7 @@ sicp_status sicp_knn(const sicp_cloud* tgt, const float* q_xyz, const uint32_t* 
   SICP_REQUIRE(tgt && idx_out && d2_out && (q_xyz || nq == 0), "null argument");
   SICP_REQUIRE(k >= 1 && k <= kMaxK, "k must be in 1..32");
   SICP_REQUIRE(tgt->layout == SICP_CLOUD_WHOLE || q_labels, "PER_CLASS target needs query labels");
+  SICP_CHECK(validate_pose7(pose7, "sicp_knn", true));
   if (nq == 0) return SICP_OK;
   SICP_CUDA(cudaSetDevice(tgt->device));
   cudaStream_t st = current_stream();

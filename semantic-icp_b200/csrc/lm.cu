@@ -14,6 +14,7 @@
 // is inverted in closed form (rank-2 Woodbury), and the 6-dof Jacobian of r = d^T M d for T*exp(delta) is
 //   J_upsilon = -2 c,   J_omega = 2 c x (p_s + C_s c),   c = R^T M d           (verified vs the 1x7 route);
 // the sweep evaluates it in the target frame and the rotation is applied once to the reduced totals (see sweep_acc).
+#include <algorithm>
 #include <cfloat>
 #include "common.cuh"
 #include "kernels.h"
@@ -21,11 +22,6 @@
 
 namespace sicp {
 
-#ifndef SICP_LM_THREADS
-#define SICP_LM_THREADS 256
-#endif
-constexpr int kLmThreads = SICP_LM_THREADS;
-constexpr int kLmWarps = kLmThreads / 32;
 constexpr int kAcc = 28;  // 21 lower-triangular H + 6 g + cost
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -59,70 +55,120 @@ __device__ __forceinline__ double det_S(const double* u, const double* v, double
 }
 
 // ------------------------------------------------------------------ K3: E-step
-// One thread per candidate pair (slot, c).  Besides the weight it GATHERS the target point and normal of the pair
-// into residual-ordered arrays, so that the many LM sweeps of the pass stream them with coalesced loads instead of
-// repeating the gather.  Gathered arrays are c-major: record (slot, c) lives at c * nslots + slot, so a sweep thread
-// that owns one source slot reads each of its kc records with a fully coalesced warp access.
-__global__ void estep_kernel(CloudView sv, CloudView tv, int algo, int kc, double eps, double gate_d2, const double* __restrict__ pose7,
-                             const int* __restrict__ stop, int* __restrict__ corr, const float* __restrict__ d2, double* __restrict__ wout,
-                             float4* __restrict__ g_pt, double* __restrict__ g_nt, RegCtl* ctl) {
+// Besides the weights it GATHERS the target point and normal of every candidate pair into residual-ordered arrays, so
+// that the many LM sweeps of the pass stream them with coalesced loads instead of repeating the gather.  Gathered
+// arrays are c-major: record (slot, c) lives at c * nslots + slot, so a sweep thread that owns one source slot reads
+// each of its kc records with a fully coalesced warp access.
+// One thread per SOURCE SLOT and its KC candidates: the source row a_s, the source point/normal and the rotated
+// normal are fetched / computed once per slot, and the KC independent gathers of the target rows a_t are in flight
+// together (16-byte loads when the row is 16-byte aligned), which is what hides the gather latency — this kernel
+// moves 261 B per candidate and computes almost nothing.
+constexpr int kEstepThreads = 128;
+template <int KC>
+__global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, CloudView tv, int algo, double eps, double gate_d2,
+                                                              const double* __restrict__ pose7, const int* __restrict__ stop,
+                                                              int* __restrict__ corr, const float* __restrict__ d2,
+                                                              double* __restrict__ wout, float4* __restrict__ g_pt,
+                                                              double* __restrict__ g_nt, RegCtl* ctl) {
   if (stop && *stop) return;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ncorr = sv.nslots * kc;
-  const bool live = r < ncorr;
-  const int slot = live ? r / kc : 0;
-  const int ro = live ? (r - slot * kc) * sv.nslots + slot : 0;
-  int ts = live ? corr[r] : -1;
-  double w = 0.0;
-  if (ts >= 0 && !((double)d2[r] < gate_d2)) { ts = -1; corr[r] = -1; }  // `distSq < 250` (gicp.hpp:70, em_icp.hpp:65)
-  if (ts >= 0) {
-    w = 1.0;
-    double pt[3], nt[3];
-    load_point(tv, ts, pt, nt);
-    g_pt[ro] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], 0.f);
-    g_nt[ro] = nt[0]; g_nt[(size_t)ncorr + ro] = nt[1]; g_nt[2 * (size_t)ncorr + ro] = nt[2];
-    if (algo == SICP_ALGO_EM) {
-      // label compatibility (em_icp.hpp:84-89) with a_p = CM^T dist_p precomputed per point
-      const int N = sv.N;
-      const double* as = sv.avec + (size_t)slot * N;
-      const double* at = tv.avec + (size_t)ts * N;
-      double prob = 0.0;
-      for (int s = 0; s < N; s++) prob += __ldg(&at[s]) * __ldg(&as[s]);
-      // Probability() -> bool (gicp_cost_function.h:75-87): weight kept iff the density is not exactly 0
-      RT P;
-      quat_to_R(pose7, P.R);
-      P.t[0] = pose7[4]; P.t[1] = pose7[5]; P.t[2] = pose7[6];
-      double ps[3], ns[3], m[3], d[3], b[3];
-      load_point(sv, slot, ps, ns);
-      for (int i = 0; i < 3; i++) {
-        m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
-        d[i] = pt[i] - (P.R[3 * i] * ps[0] + P.R[3 * i + 1] * ps[1] + P.R[3 * i + 2] * ps[2] + P.t[i]);
+  const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = gs < sv.nslots;
+  const int slot = live ? (int)gs : 0;
+  const size_t nslots = (size_t)sv.nslots, ncorr = nslots * KC;
+  int ts[KC];
+  double w[KC];
+#pragma unroll
+  for (int c = 0; c < KC; c++) {
+    const size_t r = (size_t)slot * KC + c;
+    ts[c] = live ? corr[r] : -1;
+    w[c] = 0.0;
+    if (ts[c] >= 0 && !((double)d2[r] < gate_d2)) { ts[c] = -1; corr[r] = -1; }  // `distSq < 250` (gicp.hpp:70, em_icp.hpp:65)
+  }
+  // gather the target point / normal of every kept candidate (independent loads, issued together)
+  float4 tp[KC];
+  double nt[KC][3];
+#pragma unroll
+  for (int c = 0; c < KC; c++) {
+    const int t = ts[c] >= 0 ? ts[c] : 0;
+    tp[c] = __ldg(&tv.pts[t]);
+    nt[c][0] = __ldg(&tv.nrm[t]); nt[c][1] = __ldg(&tv.nrm[(size_t)tv.nslots + t]); nt[c][2] = __ldg(&tv.nrm[2 * (size_t)tv.nslots + t]);
+    if (ts[c] >= 0) w[c] = 1.0;
+  }
+  if (algo == SICP_ALGO_EM) {
+    // label compatibility (em_icp.hpp:84-89) with a_p = CM^T dist_p precomputed per point: w = a_t . a_s, summed in
+    // ascending class order
+    const int N = sv.N;
+    const double* as = sv.avec + (size_t)slot * N;
+    const double* at[KC];
+    double prob[KC];
+#pragma unroll
+    for (int c = 0; c < KC; c++) { at[c] = tv.avec + (size_t)(ts[c] >= 0 ? ts[c] : 0) * N; prob[c] = 0.0; }
+    if ((N & 1) == 0) {  // rows start on 16-byte boundaries
+#pragma unroll 2
+      for (int s = 0; s < N; s += 2) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(as + s));
+#pragma unroll
+        for (int c = 0; c < KC; c++) {
+          const double2 t = __ldg(reinterpret_cast<const double2*>(at[c] + s));
+          prob[c] += t.x * a.x;
+          prob[c] += t.y * a.y;
+        }
       }
-      const double kappa = 1.0 - eps;
-      apply_Minv(nt, m, d, kappa, b);
+    } else {
+      for (int s = 0; s < N; s++) {
+        const double a = __ldg(&as[s]);
+#pragma unroll
+        for (int c = 0; c < KC; c++) prob[c] += __ldg(&at[c][s]) * a;
+      }
+    }
+    // Probability() -> bool (gicp_cost_function.h:75-87): weight kept iff the density is not exactly 0
+    RT P;
+    quat_to_R(pose7, P.R);
+    P.t[0] = pose7[4]; P.t[1] = pose7[5]; P.t[2] = pose7[6];
+    double ps[3], ns[3], m[3], q[3];
+    load_point(sv, slot, ps, ns);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
+      q[i] = P.R[3 * i] * ps[0] + P.R[3 * i + 1] * ps[1] + P.R[3 * i + 2] * ps[2] + P.t[i];
+    }
+    const double kappa = 1.0 - eps;
+#pragma unroll
+    for (int c = 0; c < KC; c++) {
+      if (ts[c] < 0) continue;
+      const double d[3] = {(double)tp[c].x - q[0], (double)tp[c].y - q[1], (double)tp[c].z - q[2]};
+      double b[3];
+      apply_Minv(nt[c], m, d, kappa, b);
       const double mahal = -0.5 * (d[0] * b[0] + d[1] * b[1] + d[2] * b[2]);
       // The density can only underflow to exactly 0 when exp(mahal) is near the bottom of the double range:
       // det(2 pi S) <= (2 pi)^3 * 8, so the pow factor is >= 0.022 and for mahal > -700 the product is >= 1e-306.
       // Only candidates beyond that (Mahalanobis^2 > 1400) pay for the pow / exp of the reference expression.
       if (!(mahal > -700.0)) {
         const double two_pi = 6.283185307179586;
-        const double det2pi = (two_pi * two_pi * two_pi) * det_S(nt, m, kappa);
+        const double det2pi = (two_pi * two_pi * two_pi) * det_S(nt[c], m, kappa);
         const double density = pow(det2pi, -0.5) * exp(mahal);
-        if (density == 0.0) prob *= 0.0;  // NaN stays "true" like the bool conversion
+        if (density == 0.0) prob[c] *= 0.0;  // NaN stays "true" like the bool conversion
       }
-      w = prob;
+      w[c] = prob[c];
     }
   }
+  int kept = 0;
   if (live) {
-    wout[ro] = w;
-    if (ts < 0) {  // no residual: zeroed geometry keeps the branch-free sweep finite (its weight is 0)
-      g_pt[ro] = make_float4(0.f, 0.f, 0.f, 0.f);
-      g_nt[ro] = 0.0; g_nt[(size_t)ncorr + ro] = 0.0; g_nt[2 * (size_t)ncorr + ro] = 0.0;
+#pragma unroll
+    for (int c = 0; c < KC; c++) {
+      const size_t ro = (size_t)c * nslots + slot;  // gathered arrays are c-major
+      const bool ok = ts[c] >= 0;
+      kept += ok;
+      wout[ro] = w[c];
+      // no residual: zeroed geometry keeps the branch-free sweep finite (its weight is 0)
+      g_pt[ro] = ok ? make_float4(tp[c].x, tp[c].y, tp[c].z, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g_nt[ro] = ok ? nt[c][0] : 0.0; g_nt[ncorr + ro] = ok ? nt[c][1] : 0.0; g_nt[2 * ncorr + ro] = ok ? nt[c][2] : 0.0;
     }
   }
   if (ctl) {  // residual blocks of this pass (diagnostics)
-    const int cnt = __popc(__ballot_sync(kFullMask, ts >= 0));
-    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctl->n_corr_pass, cnt);
+    kept += __shfl_xor_sync(kFullMask, kept, 16); kept += __shfl_xor_sync(kFullMask, kept, 8); kept += __shfl_xor_sync(kFullMask, kept, 4);
+    kept += __shfl_xor_sync(kFullMask, kept, 2); kept += __shfl_xor_sync(kFullMask, kept, 1);
+    if ((threadIdx.x & 31) == 0 && kept) atomicAdd(&ctl->n_corr_pass, kept);
   }
 }
 
@@ -433,6 +479,7 @@ struct LMArgs {
   LMSync* sync;
   const double* eval_pose;  // != null: evaluate once at this pose, write kAcc totals to eval_out, return
   double* eval_out;
+  cudaGraphConditionalHandle cond;  // != 0: the launch is the last node of a graph WHILE body (register.cu); set to "not converged"
 };
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
@@ -465,6 +512,15 @@ __device__ __forceinline__ void loss_fast(double w, double res, double* rho0, do
   *rho1 = f1 * (0.5 * rs);
 }
 
+// w[i] with a runtime index, without sending the array to local memory
+template <int KC>
+__device__ __forceinline__ double pick_w(const double* w, int i) {
+  double r = w[0];
+#pragma unroll
+  for (int j = 1; j < KC; j++) r = (i == j) ? w[j] : r;
+  return r;
+}
+
 // Residual sweep at the pose (P.R, P.t): one thread owns one source slot and its KC gathered records.
 // Everything is evaluated in the TARGET frame so that no per-residual R^T products are needed:
 //   d = p_t - (R p_s + t),  m = R n_s,  b = (2I - kappa(n_t n_t^T + m m^T))^-1 d,  res = d.b
@@ -474,7 +530,9 @@ __device__ __forceinline__ void loss_fast(double w, double res, double* rho0, do
 // (4, -2, 1/2) and the rotation D are applied ONCE to the 28 grid totals by the controller block.
 // The KC records of a slot are evaluated by straight-line, branch-free code (records without a residual have w = 0 and
 // zeroed geometry) so that their dependency chains interleave.
-template <int ALGO, int KC>
+// CH = records of a slot evaluated together (CH == KC: all of them, the widest interleave, needs ~240 registers;
+// CH < KC: the slot's records are taken CH at a time by a rolled loop, which fits 128 registers and twice the warps).
+template <int ALGO, int KC, int THREADS, int CH>
 __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc) {
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
@@ -485,18 +543,21 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
   const int ngroups = nslots >> 5;
   const int g0 = (int)(((long long)ngroups * blockIdx.x) / gridDim.x), g1 = (int)(((long long)ngroups * (blockIdx.x + 1)) / gridDim.x);
   const int lane = threadIdx.x & 31;
-  for (int g = g0 + (threadIdx.x >> 5); g < g1; g += kLmThreads / 32) {
+  for (int g = g0 + (threadIdx.x >> 5); g < g1; g += THREADS / 32) {
     const int slot = (g << 5) + lane;
     // every load of the slot is issued before the first use (one L2 round trip per warp-iteration)
     double w[KC];
-    float4 tp[KC];
-    double u[KC][3];
+    float4 tp[CH];
+    double u[CH][3];
 #pragma unroll
-    for (int c = 0; c < KC; c++) {
-      const size_t ro = (size_t)c * nslots + slot;
-      w[c] = __ldg(&a.w[ro]);
-      tp[c] = __ldg(&a.g_pt[ro]);
-      u[c][0] = __ldg(&a.g_nt[ro]); u[c][1] = __ldg(&a.g_nt[ncorr + ro]); u[c][2] = __ldg(&a.g_nt[2 * ncorr + ro]);
+    for (int c = 0; c < KC; c++) w[c] = __ldg(&a.w[(size_t)c * nslots + slot]);
+    if (CH == KC) {
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+        const size_t ro = (size_t)c * nslots + slot;
+        tp[c] = __ldg(&a.g_pt[ro]);
+        u[c][0] = __ldg(&a.g_nt[ro]); u[c][1] = __ldg(&a.g_nt[ncorr + ro]); u[c][2] = __ldg(&a.g_nt[2 * ncorr + ro]);
+      }
     }
     const float4 sp = __ldg(&a.sv.pts[slot]);
     double ns[3] = {__ldg(&a.sv.nrm[slot]), __ldg(&a.sv.nrm[(size_t)nslots + slot]), __ldg(&a.sv.nrm[2 * (size_t)nslots + slot])};
@@ -516,8 +577,18 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
       qt[i] = q0[i] + s_RT[9 + i];
       m[i] = r0 * ns[0] + r1 * ns[1] + r2 * ns[2];
     }
+#pragma unroll 1
+    for (int c0 = 0; c0 < KC; c0 += CH) {
+    if (CH != KC) {
 #pragma unroll
-    for (int c = 0; c < KC; c++) {
+      for (int c = 0; c < CH; c++) {
+        const size_t ro = (size_t)(c0 + c) * nslots + slot;
+        tp[c] = __ldg(&a.g_pt[ro]);
+        u[c][0] = __ldg(&a.g_nt[ro]); u[c][1] = __ldg(&a.g_nt[ncorr + ro]); u[c][2] = __ldg(&a.g_nt[2 * ncorr + ro]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
       const double d[3] = {(double)tp[c].x - qt[0], (double)tp[c].y - qt[1], (double)tp[c].z - qt[2]};
       // b = M d (rank-2 Woodbury, see apply_Minv)
       const double cuv = u[c][0] * m[0] + u[c][1] * m[1] + u[c][2] * m[2];
@@ -531,7 +602,7 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
       for (int i = 0; i < 3; i++) b[i] = 0.5 * d[i] + (g1c * u[c][i] + g2c * m[i]);
       const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
       double rho0, rho1;
-      loss_fast<ALGO>(w[c], res, &rho0, &rho1);
+      loss_fast<ALGO>(CH == KC ? w[c] : pick_w<KC>(w, c0 + c), res, &rho0, &rho1);
       const double mb = a.cfg.kappa * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]);
       const double v[3] = {q0[0] - mb * m[0], q0[1] - mb * m[1], q0[2] - mb * m[2]};
       double j[6], jw[6];
@@ -550,21 +621,24 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
       }
       acc[27] += rho0;
     }
+    }
   }
 }
 
 // Block reduction of the 28 per-thread sums through shared memory (fixed order => deterministic): every thread
 // stores its 28 values, then 28 x 8 threads each add one 32-value segment of one row (rotated start: conflict-free)
 // and a 3-step butterfly joins the 8 segments.  Leaves the block's sums in part[blockIdx.x][0..27].
+template <int THREADS>
 __device__ __forceinline__ void block_reduce(const double* acc, double* s_acc, double* part) {
+  constexpr int kLmWarps = THREADS / 32;
   const int tid = threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < kAcc; i++) s_acc[i * kLmThreads + tid] = acc[i];
+  for (int i = 0; i < kAcc; i++) s_acc[i * THREADS + tid] = acc[i];
   __syncthreads();
-  {  // kAcc * kLmWarps <= kLmThreads (kAcc < 32); every thread runs the shuffles, the surplus ones carry zeros
+  {  // kAcc * kLmWarps <= THREADS (kAcc < 32); every thread runs the shuffles, the surplus ones carry zeros
     const bool active = tid < kAcc * kLmWarps;
     const int row = active ? tid / kLmWarps : 0, seg = tid % kLmWarps;
-    const double* base = s_acc + row * kLmThreads + seg * 32;
+    const double* base = s_acc + row * THREADS + seg * 32;
     double s = 0;
     if (active) {
 #pragma unroll 8
@@ -578,7 +652,9 @@ __device__ __forceinline__ void block_reduce(const double* acc, double* s_acc, d
 
 // Fixed-order sum of the block partials by the controller block: warp `sub` sums blocks sub, sub+8, ... with
 // independent loads, then the 8 warp sums are added in order.  Result in s_tot[0..27].
+template <int THREADS>
 __device__ __forceinline__ void reduce_partials(const double* part, double (*s_red)[kAcc], double* s_tot) {
+  constexpr int kLmWarps = THREADS / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0;
   if (lane < kAcc) {
@@ -597,7 +673,7 @@ __device__ __forceinline__ void reduce_partials(const double* part, double (*s_r
   if (threadIdx.x < kAcc) {
     double t = 0;
 #pragma unroll
-    for (int wv = 0; wv < kLmThreads / 32; wv++) t += s_red[wv][threadIdx.x];
+    for (int wv = 0; wv < kLmWarps; wv++) t += s_red[wv][threadIdx.x];
     s_tot[threadIdx.x] = t;
   }
   __syncthreads();
@@ -633,11 +709,11 @@ __device__ __forceinline__ void rotate_totals(const double* s_tot, const double*
 // ONE 256-thread CTA per SM: with up to 255 registers per thread the k_c residual chains of a slot interleave without
 // spills, which feeds the FP64 pipe better than twice the warps at 128 registers (measured: 1.97 -> 1.76 ms of LM per
 // KITTI EM registration), and every CTA sees the same SM so none finishes early behind an older neighbour.
-template <int ALGO, int KC>
-__global__ void __launch_bounds__(kLmThreads, 1) lm_kernel(LMArgs a) {
-  extern __shared__ double s_acc[];  // [kAcc][kLmThreads]
+template <int ALGO, int KC, int THREADS, int MINB, int CH>
+__global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
+  extern __shared__ double s_acc[];  // [kAcc][THREADS]
   __shared__ LMState S;
-  __shared__ double s_red[kLmThreads / 32][kAcc];
+  __shared__ double s_red[THREADS / 32][kAcc];
   __shared__ double s_tot[kAcc];
   __shared__ double s_rot[kAcc];
   __shared__ double s_x[8];  // pose to evaluate [7] + done flag
@@ -650,7 +726,10 @@ __global__ void __launch_bounds__(kLmThreads, 1) lm_kernel(LMArgs a) {
   if (threadIdx.x == 7) s_x[7] = eval_only ? 0.0 : (double)a.ctl->converged;
   if (controller && threadIdx.x == 0) S.started = 0;
   __syncthreads();
-  if (s_x[7] != 0.0) return;  // registration already converged: passes enqueued ahead of the host return at once
+  if (s_x[7] != 0.0) {  // registration already converged: passes enqueued ahead of the host return at once
+    if (a.cond && controller && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0u);  // never leave a graph loop running
+    return;
+  }
   unsigned gen = ld_acquire(&sy->flag);  // generations continue across launches
   long long t_comp = 0, t_ctl = 0, t_wait = 0, t_red = 0, t_lm = 0;
   const long long t_start = clock64();
@@ -662,8 +741,8 @@ __global__ void __launch_bounds__(kLmThreads, 1) lm_kernel(LMArgs a) {
     }
     __syncthreads();
     double acc[kAcc];
-    sweep_acc<ALGO, KC>(a, s_RT, acc);
-    block_reduce(acc, s_acc, a.partials);
+    sweep_acc<ALGO, KC, THREADS, CH>(a, s_RT, acc);
+    block_reduce<THREADS>(acc, s_acc, a.partials);
     gen++;
     __syncthreads();  // the block's partial sums are written; thread 0's gpu-scope fence below is cumulative over them
     t_comp += clock64() - t0;
@@ -688,7 +767,7 @@ __global__ void __launch_bounds__(kLmThreads, 1) lm_kernel(LMArgs a) {
       __syncthreads();
       t_wait += clock64() - t0;
       t0 = clock64();
-      reduce_partials(a.partials, s_red, s_tot);
+      reduce_partials<THREADS>(a.partials, s_red, s_tot);
       rotate_totals(s_tot, s_RT, s_rot);
       __syncthreads();
       const long long t1 = clock64();
@@ -734,6 +813,7 @@ __global__ void __launch_bounds__(kLmThreads, 1) lm_kernel(LMArgs a) {
           c->last_mse = mse;
           if (conv && !(mse < a.cfg.mse_stop)) c->flags |= 1;
           c->converged = conv ? 1 : 0;
+          if (a.cond) cudaGraphSetConditional(a.cond, conv ? 0u : 1u);  // graph WHILE body: run another pass?
         }
         for (int i = 0; i < 7; i++) { s_x[i] = S.cand[i]; sy->bcast[i] = S.cand[i]; }
         s_x[7] = S.done ? 1.0 : 0.0;
@@ -804,56 +884,90 @@ __global__ void fused_labels_kernel(CloudView sv, CloudView tv, double eps, doub
 }
 
 // ------------------------------------------------------------------ host launchers
-static void* lm_entry(int algo) {
-  switch (algo) {
-    case SICP_ALGO_GICP: return (void*)lm_kernel<SICP_ALGO_GICP, 1>;
-    case SICP_ALGO_SEMANTIC: return (void*)lm_kernel<SICP_ALGO_SEMANTIC, 1>;
-    default: return (void*)lm_kernel<SICP_ALGO_EM, 4>;
+// Shapes of the LM kernel (LMConfig.variant).  0 is the lone-registration shape: one 256-thread CTA per SM with every
+// record chain of a slot interleaved (~240 registers).  The others trade per-solve speed for co-residency: a CTA that
+// leaves registers free lets the CTAs of OTHER registrations (a second solve in its control step, kNN kernels) use the
+// SM while this one waits — what a batch needs.
+struct LmShape { int threads, minb; };
+static const LmShape kLmShapes[kLmVariants] = {{256, 1}, {128, 1}, {256, 2}, {256, 2}, {512, 1}};
+template <int ALGO, int KC>
+static void* lm_entry_algo(int variant) {
+  switch (variant) {
+    case 1: return (void*)lm_kernel<ALGO, KC, 128, 1, KC>;
+    case 2: return (void*)lm_kernel<ALGO, KC, 256, 2, 1>;
+    case 3: return (void*)lm_kernel<ALGO, KC, 256, 2, (KC >= 2 ? 2 : 1)>;
+    case 4: return (void*)lm_kernel<ALGO, KC, 512, 1, 1>;
+    default: return (void*)lm_kernel<ALGO, KC, 256, 1, KC>;
   }
 }
-constexpr size_t kLmSmem = sizeof(double) * kAcc * kLmThreads;  // block_reduce staging (56 KB, opt-in dynamic shared memory)
-int lm_grid_blocks(int device) {
-  static int cached[64] = {0};
-  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+static void* lm_entry(int algo, int variant) {
+  switch (algo) {
+    case SICP_ALGO_GICP: return lm_entry_algo<SICP_ALGO_GICP, 1>(variant);
+    case SICP_ALGO_SEMANTIC: return lm_entry_algo<SICP_ALGO_SEMANTIC, 1>(variant);
+    default: return lm_entry_algo<SICP_ALGO_EM, 4>(variant);
+  }
+}
+static size_t lm_smem(int variant) { return sizeof(double) * kAcc * kLmShapes[variant].threads; }  // block_reduce staging (opt-in dynamic shared memory)
+// Largest cooperative grid of a shape on this device (co-resident CTAs), capped by the partials slab.
+int lm_max_grid(int device, int algo, int variant) {
+  static int cached[64][3][kLmVariants] = {};
+  if (variant < 0 || variant >= kLmVariants) variant = 0;
+  const int ai = algo == SICP_ALGO_GICP ? 0 : algo == SICP_ALGO_SEMANTIC ? 1 : 2;
+  if (device >= 0 && device < 64 && cached[device][ai][variant]) return cached[device][ai][variant];
   int sms = 148, per_sm = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  for (int algo : {SICP_ALGO_GICP, SICP_ALGO_SEMANTIC, SICP_ALGO_EM})
-    cudaFuncSetAttribute(lm_entry(algo), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLmSmem);
-  (void)per_sm;
-  int g = sms;  // one CTA per SM (see lm_kernel)
-  if (device >= 0 && device < 64) cached[device] = g;
+  void* fn = lm_entry(algo, variant);
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem(variant));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLmShapes[variant].threads, lm_smem(variant)) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const int g = std::min(sms * per_sm, kLmMaxGrid);
+  if (device >= 0 && device < 64) cached[device][ai][variant] = g;
   return g;
+}
+int lm_grid_blocks(int device) {  // lone-registration grid: one CTA of shape 0 per SM
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return std::min(sms, kLmMaxGrid);
 }
 
 sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, double gate_d2, const double* d_pose7,
                          const int* d_stop, int* d_corr, const float* d_d2, double* d_w, float4* d_gpt, double* d_gnt, RegCtl* d_ctl,
                          cudaStream_t st) {
-  const int n = src->nslots * cfg.kc;
-  if (n == 0) return SICP_OK;
-  estep_kernel<<<(n + 255) / 256, 256, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.kc, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w,
-                                               d_gpt, d_gnt, d_ctl);
+  if (src->nslots == 0) return SICP_OK;
+  const unsigned grid = (unsigned)((src->nslots + kEstepThreads - 1) / kEstepThreads);
+  if (cfg.kc == 4)
+    estep_kernel<4><<<grid, kEstepThreads, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w, d_gpt, d_gnt, d_ctl);
+  else
+    estep_kernel<1><<<grid, kEstepThreads, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w, d_gpt, d_gnt, d_ctl);
   count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
 }
 
 static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
+  const int variant = (args.cfg.variant >= 0 && args.cfg.variant < kLmVariants) ? args.cfg.variant : 0;
+  int dev = 0;
+  SICP_CUDA(cudaGetDevice(&dev));
+  grid = std::max(1, std::min(grid, lm_max_grid(dev, args.cfg.algo, variant)));  // also sets the shared-memory attribute
+  args.partials = reinterpret_cast<double*>(args.sync) + kLmSyncDoubles;
   void* params[] = {&args};
-  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo), dim3(grid), dim3(kLmThreads), params, kLmSmem, st));
+  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo, variant), dim3(grid), dim3(kLmShapes[variant].threads), params, lm_smem(variant), st));
   count_launches(1);
   return SICP_OK;
 }
 
+// d_partials: kLmSyncDoubles doubles of LMSync (zeroed once when the workspace is created; generations continue across
+// launches) followed by kLmMaxGrid * kAcc block partials.
 sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt, RegCtl* d_ctl,
-                      double* d_partials, int grid, cudaStream_t st) {
-  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, d_ctl, d_partials + (size_t)grid * kAcc, reinterpret_cast<LMSync*>(d_partials), nullptr, nullptr};
-  static_assert(sizeof(LMSync) <= sizeof(double) * kAcc, "LMSync must fit in the first partials slab");
+                      double* d_partials, int grid, cudaStream_t st, unsigned long long cond_handle) {
+  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, d_ctl, nullptr, reinterpret_cast<LMSync*>(d_partials), nullptr, nullptr,
+              (cudaGraphConditionalHandle)cond_handle};
+  static_assert(sizeof(LMSync) <= sizeof(double) * kLmSyncDoubles, "LMSync must fit in front of the partials");
   return launch_lm_args(args, grid, st);
 }
 
 sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt,
                             const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st) {
-  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, nullptr, d_partials + (size_t)grid * kAcc, reinterpret_cast<LMSync*>(d_partials), d_pose7, d_out28};
+  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, nullptr, nullptr, reinterpret_cast<LMSync*>(d_partials), d_pose7, d_out28, 0};
   return launch_lm_args(args, grid, st);
 }
 

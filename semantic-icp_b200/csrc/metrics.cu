@@ -91,8 +91,11 @@ sicp_status sicp_label_agreement(const sicp_cloud* src, const sicp_cloud* tgt, c
   SICP_REQUIRE(src->layout == SICP_CLOUD_WHOLE && tgt->layout == SICP_CLOUD_WHOLE, "label agreement needs WHOLE clouds");
   SICP_REQUIRE(n_labels >= 0 && (n_labels == 0 || confusion_out), "confusion_out is null");
   SICP_REQUIRE(src->device == tgt->device, "clouds live on different devices");
+  SICP_CHECK(validate_pose7(pose7, "sicp_label_agreement", true));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
+  SICP_CUDA(src->wait_built(st));
+  SICP_CUDA(tgt->wait_built(st));
   stats3_out[0] = stats3_out[1] = stats3_out[2] = 0.0;
   if (n_labels) std::memset(confusion_out, 0, sizeof(int64_t) * (size_t)n_labels * n_labels);
   if (src->nslots == 0) return SICP_OK;

@@ -1,13 +1,24 @@
-// register.cu — host orchestration of one align(): covariance precompute, then outer passes
-// [transform + kNN] -> [E-step] -> [cooperative LM solve + convergence test], all control state device-resident.
+// register.cu — host orchestration of align(): covariance precompute, then the outer loop
+// [transform + kNN] -> [E-step] -> [cooperative LM solve + convergence test] with every piece of loop state on the device.
 // Replaces the bodies of GICP::align (impl/gicp.hpp:29-175), SemanticIterativeClosestPoint::align
 // (impl/semantic_icp.hpp:27-166) and EmIterativeClosestPoint::align (impl/em_icp.hpp:24-200).
+//
+// The outer loop itself runs on the DEVICE: the three kernels of a pass are the body of a CUDA-graph WHILE node whose
+// condition the LM kernel sets from the reference's stopping rule (cudaGraphSetConditional), so a registration is ONE
+// graph launch and ONE read of the 2 KB control block at the end — no host round trip between passes.  Registrations
+// run in SLOTS: a slot owns a stream, a persistent workspace (no allocation per registration) and its graph exec, and the
+// batch executor keeps `max_concurrent` slots busy; the host sleeps on a completion queue fed by stream callbacks.
+// The pass-by-pass path (kernels enqueued in chunks, control block read back between chunks) remains for
+// options.profile (per-stage CUDA events cannot live inside a graph) and as the fallback when SICP_GRAPH=0.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -15,6 +26,19 @@
 #include "kernels.h"
 
 namespace sicp {
+
+// Batch defaults (tuned on one B200; the environment variables of the same purpose override them for
+// tuning runs): registrations in flight, LM kernel shape and LM grid of a solve that shares the GPU.
+constexpr int kBatchConcurrent = 8;
+constexpr int kBatchLmVariant = 0;
+constexpr int kBatchLmGrid = 37;
+constexpr int kGraphReuse = 1;  // 1: keep one graph exec per slot and update it in place for every registration
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (!e || !*e) return dflt;
+  return atoi(e);
+}
 
 static LMConfig make_cfg(int algo, const sicp_options& o) {
   LMConfig c;
@@ -25,6 +49,7 @@ static LMConfig make_cfg(int algo, const sicp_options& o) {
   c.max_iter = o.max_lm_iterations;
   c.mse_stop = algo == SICP_ALGO_SEMANTIC ? 1e-3 : 1e-5;    // semantic_icp.hpp:152 / gicp.hpp:154, em_icp.hpp:180
   c.outer_cap = algo == SICP_ALGO_SEMANTIC ? 35 : 50;
+  c.variant = 0;
   return c;
 }
 
@@ -39,10 +64,16 @@ static sicp_status validate(int algo, const sicp_cloud* src, const sicp_cloud* t
     SICP_REQUIRE(src->has_labels && tgt->has_labels, "EM needs labelled clouds");
   }
   SICP_REQUIRE(o->k_cov >= 1 && o->k_cov <= kMaxK, "k_cov must be in 1..32");
+  SICP_REQUIRE((long long)src->nslots * 4 < (1ll << 31), "source cloud too large for one registration (nslots * 4 must fit 31 bits)");
   return SICP_OK;
 }
-// Sophus::SE3d is a unit quaternion by construction; a pose7 coming through the C ABI has to be checked
-static sicp_status validate_pose(const double* p7, const char* what) {
+
+sicp_status validate_pose7(const double* p7, const char* what, bool nullable) {
+  if (!p7) {
+    if (nullable) return SICP_OK;
+    set_error(std::string(what) + ": pose7 is null");
+    return SICP_ERR_INVALID;
+  }
   double n2 = 0;
   bool finite = true;
   for (int i = 0; i < 7; i++) finite = finite && std::isfinite(p7[i]);
@@ -52,28 +83,18 @@ static sicp_status validate_pose(const double* p7, const char* what) {
 }
 
 // Covariances / label vectors of both clouds of a pair.  The two clouds are independent, and one covariance kernel is
-// a single wave with a long tail (a few slow warps), so the target runs on a helper stream beside the source on `st`;
-// `st` then waits for the target's ready event.  slot: index of the helper stream, or -1 to run both on `st` — the batch
-// executor does that: with 8 registrations in flight the tails are already filled by other registrations and the extra
-// streams cost 2-4 % of throughput (measured), while a lone registration gains 0.35 ms (cov stage 1.05 -> 0.70 ms).
-static thread_local std::vector<cudaStream_t> t_helpers;
-static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* o, cudaStream_t st, int slot) {
+// a single wave with a long tail (a few slow warps), so for a LONE registration the target runs on a helper stream
+// beside the source on `st`; `st` then waits for both ready events.  In a batch (helper == nullptr) both run on `st`:
+// the tails are already filled by the other registrations in flight.
+static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* o, cudaStream_t st, cudaStream_t helper) {
   const int N = algo == SICP_ALGO_EM ? o->n_classes : 0;
   cudaStream_t saved = current_stream();
   sicp_status rc = SICP_OK;
-  if (tgt != src && !tgt->pre_valid && slot >= 0) {
-    while ((int)t_helpers.size() <= slot) {
-      cudaStream_t h;
-      SICP_CUDA(cudaStreamCreateWithFlags(&h, cudaStreamNonBlocking));
-      t_helpers.push_back(h);
-    }
-    cudaStream_t h = t_helpers[slot];
-    if (tgt->built_ev) SICP_CUDA(cudaStreamWaitEvent(h, tgt->built_ev, 0));
-    sicp_set_stream(h);
+  if (tgt != src) {
+    bool cached;
+    { std::lock_guard<std::mutex> lk(tgt->mu); cached = tgt->pre_valid; }
+    sicp_set_stream(helper && !cached ? helper : st);
     rc = sicp_cloud_precompute(tgt, o->k_cov, o->epsilon, N, o->confusion);
-  } else if (tgt != src) {
-    sicp_set_stream(st);
-    rc = sicp_cloud_precompute(tgt, o->k_cov, o->epsilon, N, o->confusion);  // cached: checks the parameters only
   }
   if (rc == SICP_OK) {
     sicp_set_stream(st);
@@ -81,62 +102,107 @@ static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, c
   }
   sicp_set_stream(saved);
   SICP_CHECK(rc);
-  if (src->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, src->ready_ev, 0));
-  if (tgt->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, tgt->ready_ev, 0));
+  SICP_CUDA(src->wait_ready(st));
+  SICP_CUDA(tgt->wait_ready(st));
   return SICP_OK;
 }
 
-// Pinned control blocks are pooled: cudaMallocHost / cudaFreeHost synchronise the device and would serialise
-// concurrent registrations.
-static std::mutex g_pin_mu;
-static std::vector<RegCtl*> g_pin_free;
-static RegCtl* pin_get() {
-  {
-    std::lock_guard<std::mutex> lk(g_pin_mu);
-    if (!g_pin_free.empty()) { RegCtl* p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
-  }
-  RegCtl* p = nullptr;
-  if (cudaMallocHost(&p, sizeof(RegCtl)) != cudaSuccess) return nullptr;
-  return p;
-}
-static void pin_put(RegCtl* p) { std::lock_guard<std::mutex> lk(g_pin_mu); g_pin_free.push_back(p); }
-
-// Per-registration device workspace
-struct Workspace {
-  int* d_corr = nullptr; float* d_d2 = nullptr; double* d_w = nullptr; float4* d_gpt = nullptr; double* d_gnt = nullptr; RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
-  RegCtl* h_ctl = nullptr;  // pinned
-  int grid = 0;
-  cudaStream_t st = nullptr;
-  sicp_status alloc(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, int min_class_points, cudaStream_t s) {
-    st = s;
-    const size_t nc = (size_t)std::max(1, src->nslots) * cfg.kc;
-    grid = lm_grid_blocks(src->device);
-    SICP_CUDA(cudaMallocAsync(&d_corr, sizeof(int) * nc, st));
-    SICP_CUDA(cudaMallocAsync(&d_d2, sizeof(float) * nc, st));
-    SICP_CUDA(cudaMallocAsync(&d_w, sizeof(double) * nc, st));
-    SICP_CUDA(cudaMallocAsync(&d_gpt, sizeof(float4) * nc, st));
-    SICP_CUDA(cudaMallocAsync(&d_gnt, sizeof(double) * 3 * nc, st));
-    SICP_CUDA(cudaMallocAsync(&d_ctl, sizeof(RegCtl), st));
-    SICP_CUDA(cudaMallocAsync(&d_partials, sizeof(double) * 2 * 28 * grid, st));  // slab 0: LMSync (zeroed), slab 1: block partials
-    SICP_CUDA(cudaMemsetAsync(d_partials, 0, sizeof(double) * 28 * grid, st));
-    h_ctl = pin_get();
-    if (!h_ctl) { set_error("pinned allocation failed"); return SICP_ERR_CUDA; }
-    if (cfg.algo == SICP_ALGO_SEMANTIC) SICP_CHECK(make_class_map(src, tgt, min_class_points, &d_map, st));
-    return SICP_OK;
-  }
-  void release() {
-    if (d_corr) cudaFreeAsync(d_corr, st);
-    if (d_d2) cudaFreeAsync(d_d2, st);
-    if (d_w) cudaFreeAsync(d_w, st);
-    if (d_gpt) cudaFreeAsync(d_gpt, st);
-    if (d_gnt) cudaFreeAsync(d_gnt, st);
-    if (d_ctl) cudaFreeAsync(d_ctl, st);
-    if (d_partials) cudaFreeAsync(d_partials, st);
-    if (d_map) cudaFreeAsync(d_map, st);
-    if (h_ctl) pin_put(h_ctl);
-    *this = Workspace();
+// ------------------------------------------------------------------ completion queue (stream callbacks -> host)
+struct Completion {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<int> q;
+  void push(int v) { { std::lock_guard<std::mutex> lk(mu); q.push_back(v); } cv.notify_one(); }
+  int pop() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !q.empty(); });
+    const int v = q.front();
+    q.pop_front();
+    return v;
   }
 };
+struct SlotNote { Completion* c; int slot; };
+static void CUDART_CB note_done(void* p) {  // runs on a CUDA-internal thread: no CUDA calls here
+  SlotNote* n = static_cast<SlotNote*>(p);
+  n->c->push(n->slot);
+}
+
+// ------------------------------------------------------------------ slots
+// A slot is everything one registration in flight needs, kept across registrations and across calls (per host thread
+// and device): stream, workspace sized for the largest source cloud seen, pinned control block, graph exec.
+struct Slot {
+  int device = -1;
+  cudaStream_t st = nullptr;      // own stream (batch) — a lone registration runs on the caller's stream instead
+  cudaStream_t cap = nullptr;     // capture-only stream for building the pass graph
+  size_t cap_nc = 0;              // capacity in candidate records
+  int* d_corr = nullptr; float* d_d2 = nullptr; double* d_w = nullptr; float4* d_gpt = nullptr; double* d_gnt = nullptr;
+  RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
+  RegCtl* h_ctl = nullptr;        // pinned
+  int* h_map = nullptr;           // pinned, kMaxSegMap ints (class map staging)
+  cudaGraphExec_t exec = nullptr;
+  SlotNote note{nullptr, 0};
+  static constexpr int kMaxSegMap = 256;
+
+  sicp_status ensure(int dev, size_t nc) {
+    if (device != dev) { destroy(); device = dev; }
+    SICP_CUDA(cudaSetDevice(dev));
+    if (!st) SICP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (!cap) SICP_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    if (!d_ctl) {
+      SICP_CUDA(cudaMalloc(&d_ctl, sizeof(RegCtl)));
+      SICP_CUDA(cudaMalloc(&d_partials, sizeof(double) * kLmPartialsDoubles));
+      SICP_CUDA(cudaMemset(d_partials, 0, sizeof(double) * kLmPartialsDoubles));  // LMSync starts at zero; generations continue from there
+      SICP_CUDA(cudaMalloc(&d_map, sizeof(int) * kMaxSegMap));
+      SICP_CUDA(cudaMallocHost(&h_ctl, sizeof(RegCtl)));
+      SICP_CUDA(cudaMallocHost(&h_map, sizeof(int) * kMaxSegMap));
+    }
+    nc = std::max<size_t>(nc, 1);
+    if (nc > cap_nc) {
+      // growing is rare (largest source cloud seen so far); the old buffers may still be referenced by work in flight
+      SICP_CUDA(cudaDeviceSynchronize());
+      free_records();
+      const size_t want = nc + nc / 8;
+      SICP_CUDA(cudaMalloc(&d_corr, sizeof(int) * want));
+      SICP_CUDA(cudaMalloc(&d_d2, sizeof(float) * want));
+      SICP_CUDA(cudaMalloc(&d_w, sizeof(double) * want));
+      SICP_CUDA(cudaMalloc(&d_gpt, sizeof(float4) * want));
+      SICP_CUDA(cudaMalloc(&d_gnt, sizeof(double) * 3 * want));
+      cap_nc = want;
+    }
+    return SICP_OK;
+  }
+  void free_records() {
+    cudaFree(d_corr); cudaFree(d_d2); cudaFree(d_w); cudaFree(d_gpt); cudaFree(d_gnt);
+    d_corr = nullptr; d_d2 = nullptr; d_w = nullptr; d_gpt = nullptr; d_gnt = nullptr; cap_nc = 0;
+  }
+  void destroy() {
+    if (device < 0) return;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }  // context already gone (process exit)
+    if (exec) cudaGraphExecDestroy(exec);
+    free_records();
+    cudaFree(d_ctl); cudaFree(d_partials); cudaFree(d_map);
+    if (h_ctl) cudaFreeHost(h_ctl);
+    if (h_map) cudaFreeHost(h_map);
+    if (st) cudaStreamDestroy(st);
+    if (cap) cudaStreamDestroy(cap);
+    cudaGetLastError();
+    *this = Slot();
+  }
+};
+struct SlotPool {
+  std::vector<Slot*> slots;
+  Slot* get(int i) {
+    while ((int)slots.size() <= i) slots.push_back(new Slot());
+    return slots[i];
+  }
+  ~SlotPool() { for (Slot* s : slots) { s->destroy(); delete s; } }
+};
+static thread_local SlotPool t_pool;
+static thread_local cudaStream_t t_helper = nullptr;  // target covariances of a lone registration
+
+// graph path switch: SICP_GRAPH=0 disables it; it also turns itself off for the process if the driver rejects the graph
+static std::atomic<int> g_graph_ok{1};
+static bool graph_enabled() { return g_graph_ok.load() == 1 && env_int("SICP_GRAPH", 1) != 0; }
 
 struct StageTimer {
   bool on = false;
@@ -164,54 +230,108 @@ struct StageTimer {
 
 // One registration as a resumable state machine so that several can be interleaved on different streams.
 struct Job {
-  int algo; sicp_cloud* src; sicp_cloud* tgt; const sicp_options* opts; LMConfig cfg; Workspace ws; StageTimer tm;
-  sicp_result* out; int enqueued = 0; bool finished = false; int launches = 0; int d2h = 0;
-
-  sicp_status start(const double* init7, cudaStream_t st, int lm_grid) {
-    cfg = make_cfg(algo, *opts);
-    tm.on = opts->profile != 0;
-    SICP_CHECK(ws.alloc(src, tgt, cfg, opts->min_class_points, st));
-    ws.grid = lm_grid;
-    std::memset(ws.h_ctl, 0, sizeof(RegCtl));
-    std::memcpy(ws.h_ctl->pose, init7, 56);
-    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
-    return SICP_OK;
-  }
-  static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-  double host_ms[4] = {0, 0, 0, 0};  // host time inside the launch calls of this job (kNN, E-step, LM, readback): diagnostics
-  sicp_status enqueue_pass() {
-    cudaStream_t st = ws.st;
-    const int* stop = &ws.d_ctl->converged;
-    double h0 = now_ms();
-    tm.begin(SICP_STAGE_KNN, st);
-    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, stop, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
-    tm.end(st);
-    host_ms[0] += now_ms() - h0; h0 = now_ms();
-    tm.begin(SICP_STAGE_ESTEP, st);
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, stop, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, ws.d_ctl, st));
-    tm.end(st);
-    host_ms[1] += now_ms() - h0; h0 = now_ms();
-    tm.begin(SICP_STAGE_LM, st);
-    SICP_CHECK(launch_lm(src, cfg, ws.d_w, ws.d_gpt, ws.d_gnt, ws.d_ctl, ws.d_partials, ws.grid, st));
-    tm.end(st);
-    host_ms[2] += now_ms() - h0;
-    launches += 3;
-    enqueued++;
-    return SICP_OK;
-  }
-  // enqueue a chunk of passes, then the control-block readback
-  sicp_status enqueue_chunk(int n) {
-    const int cap = cfg.outer_cap + 2;
-    for (int i = 0; i < n && enqueued < cap; i++) SICP_CHECK(enqueue_pass());
-    SICP_CUDA(cudaMemcpyAsync(ws.h_ctl, ws.d_ctl, sizeof(RegCtl), cudaMemcpyDeviceToHost, ws.st));
-    d2h += (int)sizeof(RegCtl);
-    return SICP_OK;
-  }
-  // after the stream is synchronised: true when the registration is complete
-  bool done_after_sync() const { return ws.h_ctl->converged != 0 || enqueued >= cfg.outer_cap + 2; }
+  int algo; sicp_cloud* src; sicp_cloud* tgt; const sicp_options* opts; LMConfig cfg; StageTimer tm;
+  sicp_result* out; Slot* sl = nullptr; cudaStream_t st = nullptr; int lm_grid = 0;
+  int enqueued = 0; bool finished = false; bool graphed = false; int d2h = 0;
   cudaEvent_t trace_ref = nullptr; int trace_id = 0;
+
+  // class map of SemanticICP (semantic_icp.hpp:50-51) through the slot's pinned staging: no host synchronisation
+  sicp_status stage_class_map() {
+    if (cfg.algo != SICP_ALGO_SEMANTIC) return SICP_OK;
+    SICP_REQUIRE(src->nseg <= Slot::kMaxSegMap, "too many classes");
+    for (int s = 0; s < src->nseg; s++) {
+      int m = -1;
+      if (src->h_seg[s].n > opts->min_class_points)
+        for (int t = 0; t < tgt->nseg; t++)
+          if (tgt->class_labels[t] == src->class_labels[s]) { m = t; break; }
+      sl->h_map[s] = m;
+    }
+    SICP_CUDA(cudaMemcpyAsync(sl->d_map, sl->h_map, sizeof(int) * std::max(1, src->nseg), cudaMemcpyHostToDevice, st));
+    return SICP_OK;
+  }
+  sicp_status start(const double* init7) {
+    SICP_CHECK(stage_class_map());
+    std::memset(sl->h_ctl, 0, sizeof(RegCtl));
+    std::memcpy(sl->h_ctl->pose, init7, 56);
+    SICP_CUDA(cudaMemcpyAsync(sl->d_ctl, sl->h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+    return SICP_OK;
+  }
+  const int* class_map() const { return cfg.algo == SICP_ALGO_SEMANTIC ? sl->d_map : nullptr; }
+  // the three kernels of one outer pass on stream `s` (the slot's stream, or the capture stream of the graph build)
+  sicp_status enqueue_pass(cudaStream_t s, unsigned long long cond) {
+    const int* stop = &sl->d_ctl->converged;
+    tm.begin(SICP_STAGE_KNN, s);
+    SICP_CHECK(launch_cross_knn(src, tgt, sl->d_ctl->pose, stop, class_map(), cfg.kc, sl->d_corr, sl->d_d2, s));
+    tm.end(s);
+    tm.begin(SICP_STAGE_ESTEP, s);
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, sl->d_ctl->pose, stop, sl->d_corr, sl->d_d2, sl->d_w, sl->d_gpt, sl->d_gnt, sl->d_ctl, s));
+    tm.end(s);
+    tm.begin(SICP_STAGE_LM, s);
+    SICP_CHECK(launch_lm(src, cfg, sl->d_w, sl->d_gpt, sl->d_gnt, sl->d_ctl, sl->d_partials, lm_grid, s, cond));
+    tm.end(s);
+    return SICP_OK;
+  }
+  // ---- device-resident outer loop: WHILE(not converged) { kNN, E-step, LM } as one graph launch
+  sicp_status launch_graph() {
+    cudaGraph_t g = nullptr;
+    SICP_CUDA(cudaGraphCreate(&g, 0));
+    auto build = [&]() -> sicp_status {
+      cudaGraphConditionalHandle h;
+      SICP_CUDA(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));  // every launch starts with "run a pass"
+      cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+      cp.conditional.handle = h;
+      cp.conditional.type = cudaGraphCondTypeWhile;
+      cp.conditional.size = 1;
+      cudaGraphNode_t node;
+      SICP_CUDA(cudaGraphAddNode(&node, g, nullptr, 0, &cp));
+      cudaGraph_t body = cp.conditional.phGraph_out[0];
+      SICP_CUDA(cudaStreamBeginCaptureToGraph(sl->cap, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+      const sicp_status rc = enqueue_pass(sl->cap, (unsigned long long)h);
+      cudaGraph_t ended = nullptr;
+      const cudaError_t e = cudaStreamEndCapture(sl->cap, &ended);
+      SICP_CHECK(rc);
+      SICP_CUDA(e);
+      const int reuse = env_int("SICP_GRAPH_REUSE", kGraphReuse);
+      if (sl->exec && reuse) {  // same topology as the previous registration of this slot: update the kernel parameters in place
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(sl->exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(sl->exec); sl->exec = nullptr; }
+      } else if (sl->exec) {
+        cudaGraphExecDestroy(sl->exec);  // the previous registration of this slot has completed (its readback was consumed)
+        sl->exec = nullptr;
+      }
+      if (!sl->exec) SICP_CUDA(cudaGraphInstantiate(&sl->exec, g, 0));
+      SICP_CUDA(cudaGraphLaunch(sl->exec, st));
+      return SICP_OK;
+    };
+    const sicp_status rc = build();
+    cudaGraphDestroy(g);
+    if (rc == SICP_OK) { graphed = true; enqueued = cfg.outer_cap + 2; }
+    return rc;
+  }
+  // enqueue the rest of the registration (graph) or a chunk of passes (pass-by-pass path), then the control-block
+  // readback and the completion callback
+  sicp_status advance(int chunk) {
+    bool done = false;
+    if (!graphed && !tm.on && enqueued == 0 && graph_enabled()) {
+      if (launch_graph() == SICP_OK) done = true;
+      else {
+        cudaGetLastError();
+        if (g_graph_ok.exchange(0) == 1) fprintf(stderr, "[sicp] graph outer loop unavailable (%s); using the pass-by-pass path\n", sicp_last_error());
+      }
+    }
+    if (!done) {
+      const int cap = cfg.outer_cap + 2;
+      for (int i = 0; i < chunk && enqueued < cap; i++) { SICP_CHECK(enqueue_pass(st, 0)); enqueued++; }
+    }
+    SICP_CUDA(cudaMemcpyAsync(sl->h_ctl, sl->d_ctl, sizeof(RegCtl), cudaMemcpyDeviceToHost, st));
+    d2h += (int)sizeof(RegCtl);
+    if (sl->note.c) SICP_CUDA(cudaLaunchHostFunc(st, note_done, &sl->note));
+    return SICP_OK;
+  }
+  // after the readback has landed: true when the registration is complete
+  bool complete() const { return sl->h_ctl->converged != 0 || enqueued >= cfg.outer_cap + 2; }
   void finish() {
-    const RegCtl& c = *ws.h_ctl;
+    const RegCtl& c = *sl->h_ctl;
     std::memcpy(out->pose7, c.pose, 56);
     out->outer_iter = c.outer; out->lm_iters_total = c.lm_iters_total; out->final_cost = c.final_cost; out->n_corr_last = c.n_corr_last;
     out->flags = c.flags; out->lm_evals_total = c.lm_evals_total;
@@ -221,116 +341,105 @@ struct Job {
     out->d2h_bytes = d2h;
     for (int i = 0; i < 3; i++) out->lm_cycles[i] = (double)c.dbg_cycles[i];
     for (int i = 0; i < 3; i++) out->lm_cycles[3 + i] = (double)c.dbg_cycles[4 + i];
-    out->gpu_launches = c.outer * 3;  // kernels that did work (passes enqueued past convergence return immediately)
+    out->gpu_launches = c.outer * 3;  // kernels that did work (the graph loop launches exactly these; the pass-by-pass path may add early-exit launches)
+    if (graphed) count_launches(c.outer * 3 - 3);  // the capture counted one pass
     tm.collect(out, trace_ref, trace_id);
-    ws.release();
     finished = true;
   }
 };
 
-// Streams of the batch executor are created once per host thread and reused.
-static thread_local std::vector<cudaStream_t> t_streams;
-
-// Runs all jobs with up to `max_concurrent` registrations in flight, each on its own stream.  A slot that finishes
-// immediately picks up the next job (no wave barrier), so tails of one registration overlap the bulk of another.
+// Runs all jobs with up to `max_concurrent` registrations in flight, each in its own slot.  A slot that finishes
+// immediately picks up the next job (no wave barrier), so the tail of one registration overlaps the bulk of another.
 static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int max_concurrent) {
   cudaStream_t base = current_stream();
   const int nj = (int)jobs.size();
   const int S = std::max(1, std::min(max_concurrent, nj));
-  std::vector<cudaStream_t> streams(S, base);
+  const int device = jobs[0].src->device;
+  const bool lone = S == 1;
+  size_t nc_max = 1;
+  for (const Job& jb : jobs) nc_max = std::max(nc_max, (size_t)jb.src->nslots * (jb.algo == SICP_ALGO_EM ? 4 : 1));
+  Completion done_q;
   cudaEvent_t fork = nullptr;
-  if (S > 1) {
-    while ((int)t_streams.size() < S) {
-      cudaStream_t s;
-      SICP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-      t_streams.push_back(s);
-    }
+  for (int s = 0; s < S; s++) {
+    Slot* sl = t_pool.get(s);
+    SICP_CHECK(sl->ensure(device, nc_max));
+    sl->note = SlotNote{&done_q, s};
+  }
+  if (lone && !t_helper) SICP_CUDA(cudaStreamCreateWithFlags(&t_helper, cudaStreamNonBlocking));
+  if (!lone) {
     SICP_CUDA(cudaEventCreate(&fork));
     SICP_CUDA(cudaEventRecord(fork, base));
-    for (int s = 0; s < S; s++) streams[s] = t_streams[s];  // each job waits for ITS clouds (built_ev), not for the whole base stream
   }
+  const int kChunk = std::max(1, env_int("SICP_CHUNK", 3));  // pass-by-pass path: passes enqueued between two readbacks
+  // LM kernel shape.  A lone solve takes every SM (shape 0, one 256-thread CTA each).  Concurrent solves use a shape
+  // that leaves registers free on its SMs and a grid of a fraction of the machine: their sweeps are longer, so the
+  // latency-bound control step between sweeps idles a smaller share of the SMs, and the kNN / covariance kernels of
+  // the other registrations in flight share those SMs.
+  const int variant = lone ? 0 : std::min(std::max(env_int("SICP_LM_VARIANT", kBatchLmVariant), 0), kLmVariants - 1);
   sicp_status rc = SICP_OK;
-  int kChunk = 3;  // passes enqueued between two readbacks of the control block
-  if (const char* e = getenv("SICP_CHUNK")) { const int v = atoi(e); if (v > 0) kChunk = v; }
-  // A lone solve takes every SM (one CTA each).  Concurrent solves get a quarter of the SMs each: their sweeps are longer,
-  // so the latency-bound control step between sweeps idles a smaller share of the machine, and the kNN kernels of other
-  // registrations run on the SMs no solve occupies.
-  int lm_grid = lm_grid_blocks(jobs[0].src->device) / (S > 1 ? 4 : 1);
-  if (const char* e = getenv("SICP_LM_GRID")) { const int g = atoi(e); if (g > 0 && S > 1) lm_grid = std::min(g, lm_grid_blocks(jobs[0].src->device)); }
   std::vector<int> slot_job(S, -1);
   int next = 0, live = 0;
   auto launch = [&](int slot) -> sicp_status {
     const int j = next++;
     slot_job[slot] = j;
     Job& jb = jobs[j];
-    cudaStream_t st = streams[slot];
-    // covariances / label vectors on this job's stream (no-op when cached); other jobs sharing a cloud wait on its event
+    Slot* sl = t_pool.get(slot);
+    jb.sl = sl;
+    jb.st = lone ? base : sl->st;
+    jb.cfg = make_cfg(jb.algo, *jb.opts);
+    jb.cfg.variant = variant;
+    const int gmax = lm_max_grid(device, jb.algo, variant);
+    jb.lm_grid = lone ? lm_grid_blocks(device) : std::min(gmax, std::max(1, env_int("SICP_LM_GRID", kBatchLmGrid)));
     jb.tm.on = jb.opts->profile != 0;
     jb.trace_ref = fork; jb.trace_id = j;
-    if (st != base) {  // the clouds may still be building on the stream that created them
-      if (jb.src->built_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.src->built_ev, 0));
-      if (jb.tgt->built_ev) SICP_CUDA(cudaStreamWaitEvent(st, jb.tgt->built_ev, 0));
-    }
-    jb.tm.begin(SICP_STAGE_COV, st);
-    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, st, S == 1 ? 0 : -1);
-    jb.tm.end(st);
+    // the clouds may still be building on the stream (or host thread) that created them
+    SICP_CUDA(jb.src->wait_built(jb.st));
+    SICP_CUDA(jb.tgt->wait_built(jb.st));
+    jb.tm.begin(SICP_STAGE_COV, jb.st);
+    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, jb.st, lone ? t_helper : nullptr);
+    jb.tm.end(jb.st);
     SICP_CHECK(r);
-    SICP_CHECK(jb.start(init7s + 7 * (size_t)j, st, lm_grid));
-    SICP_CHECK(jb.enqueue_chunk(kChunk));
+    SICP_CHECK(jb.start(init7s + 7 * (size_t)j));
+    SICP_CHECK(jb.advance(kChunk));
     live++;
     return SICP_OK;
   };
-  // one completion event per slot, recorded after the control-block readback of each chunk.  The host POLLS the slots
-  // (cudaEventQuery) and serves whichever registration finished its chunk first; blocking on one stream would leave
-  // the streams of registrations that are already waiting for their next chunk empty.
-  std::vector<cudaEvent_t> ev(S, nullptr);
-  for (int s = 0; s < S; s++) SICP_CUDA(cudaEventCreateWithFlags(&ev[s], cudaEventDisableTiming));
-  auto launch_and_mark = [&](int slot) -> sicp_status {
-    SICP_CHECK(launch(slot));
-    SICP_CUDA(cudaEventRecord(ev[slot], streams[slot]));
-    return SICP_OK;
-  };
-  for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch_and_mark(s);
+  for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch(s);
   while (live > 0 && rc == SICP_OK) {
-    bool served = false;
-    for (int s = 0; s < S && rc == SICP_OK; s++) {
-      const int j = slot_job[s];
-      if (j < 0) continue;
-      const cudaError_t q = S == 1 ? cudaEventSynchronize(ev[s]) : cudaEventQuery(ev[s]);
-      if (q == cudaErrorNotReady) continue;
-      if (q != cudaSuccess) { set_error(std::string("stream failed: ") + cudaGetErrorString(q)); rc = SICP_ERR_CUDA; break; }
-      served = true;
-      if (jobs[j].done_after_sync()) {
-        jobs[j].finish();
-        live--;
-        slot_job[s] = -1;
-        if (next < nj) rc = launch_and_mark(s);
-      } else {
-        rc = jobs[j].enqueue_chunk(kChunk);
-        if (rc == SICP_OK && cudaEventRecord(ev[s], streams[s]) != cudaSuccess) { set_error("event record failed"); rc = SICP_ERR_CUDA; }
-      }
+    const int s = done_q.pop();  // sleeps until some slot's readback has landed
+    const int j = slot_job[s];
+    if (j < 0) continue;
+    if (jobs[j].complete()) {
+      jobs[j].finish();
+      live--;
+      slot_job[s] = -1;
+      if (next < nj) rc = launch(s);
+    } else {
+      rc = jobs[j].advance(kChunk);
     }
-    if (!served && rc == SICP_OK) std::this_thread::yield();
   }
-  for (int s = 0; s < S; s++) if (ev[s]) cudaEventDestroy(ev[s]);
-  if (getenv("SICP_TRACE")) {
-    double h[3] = {0, 0, 0};
-    for (Job& jb : jobs) for (int i = 0; i < 3; i++) h[i] += jb.host_ms[i];
-    fprintf(stderr, "[sicp] host ms inside launches: kNN %.2f E-step %.2f LM %.2f (all jobs)\n", h[0], h[1], h[2]);
-  }
-  if (rc != SICP_OK) cudaDeviceSynchronize();  // error path: nothing may still be writing a pinned control block we are about to recycle
-  for (Job& jb : jobs) if (!jb.finished && jb.ws.st) jb.ws.release();
-  if (S > 1) {
-    for (int s = 0; s < S; s++) {
+  if (rc != SICP_OK) cudaDeviceSynchronize();  // error path: nothing may still be writing a pinned control block
+  for (int s = 0; s < S; s++) t_pool.get(s)->note.c = nullptr;
+  if (!lone) {
+    for (int s = 0; s < S; s++) {  // join: later work on the caller's stream sees the results of every slot
       cudaEvent_t e;
       cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-      cudaEventRecord(e, streams[s]);
+      cudaEventRecord(e, t_pool.get(s)->st);
       cudaStreamWaitEvent(base, e, 0);
       cudaEventDestroy(e);
     }
     cudaEventDestroy(fork);
   }
   return rc;
+}
+
+// a slot for the synchronous single-pass entry points below (no registration of this thread is in flight when they run)
+static sicp_status scratch_slot(const sicp_cloud* src, int kc, Slot** out) {
+  Slot* sl = t_pool.get(0);
+  SICP_CHECK(sl->ensure(src->device, (size_t)src->nslots * kc));
+  sl->note.c = nullptr;
+  *out = sl;
+  return SICP_OK;
 }
 
 }  // namespace sicp
@@ -353,20 +462,12 @@ void sicp_options_default(int algo, sicp_options* o) {
 sicp_status sicp_register(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* init7, sicp_result* out) {
   SICP_REQUIRE(init7 && out, "null argument");
   SICP_CHECK(validate(algo, src, tgt, opts));
-  SICP_CHECK(validate_pose(init7, "sicp_register"));
+  SICP_CHECK(validate_pose7(init7, "sicp_register"));
   SICP_CUDA(cudaSetDevice(src->device));
-  cudaStream_t st = current_stream();
   std::memset(out, 0, sizeof *out);
-  StageTimer pre;
-  pre.on = opts->profile != 0;
-  pre.begin(SICP_STAGE_COV, st);
-  SICP_CHECK(precompute_pair(algo, src, tgt, opts, st, 0));
-  pre.end(st);
   std::vector<Job> jobs(1);
   jobs[0].algo = algo; jobs[0].src = src; jobs[0].tgt = tgt; jobs[0].opts = opts; jobs[0].out = out;
-  sicp_status rc = run_jobs(jobs, init7, 1);
-  if (rc == SICP_OK) pre.collect(out);
-  return rc;
+  return run_jobs(jobs, init7, 1);
 }
 
 sicp_status sicp_register_batch(int algo, size_t n_pairs, sicp_cloud* const* src, sicp_cloud* const* tgt, const sicp_options* opts,
@@ -376,47 +477,44 @@ sicp_status sicp_register_batch(int algo, size_t n_pairs, sicp_cloud* const* src
   for (size_t i = 0; i < n_pairs; i++) {
     SICP_CHECK(validate(algo, src[i], tgt[i], opts));
     SICP_REQUIRE(src[i]->device == src[0]->device, "all pairs of a batch must live on one device");
-    SICP_CHECK(validate_pose(init7s + 7 * i, "sicp_register_batch"));
+    SICP_CHECK(validate_pose7(init7s + 7 * i, "sicp_register_batch"));
   }
   SICP_CUDA(cudaSetDevice(src[0]->device));
   std::memset(out, 0, sizeof(sicp_result) * n_pairs);
   std::vector<Job> jobs(n_pairs);
   for (size_t i = 0; i < n_pairs; i++) { jobs[i].algo = algo; jobs[i].src = src[i]; jobs[i].tgt = tgt[i]; jobs[i].opts = opts; jobs[i].out = out + i; }
-  return run_jobs(jobs, init7s, opts->max_concurrent > 0 ? opts->max_concurrent : 8);
+  int conc = opts->max_concurrent > 0 ? opts->max_concurrent : env_int("SICP_CONCURRENT", kBatchConcurrent);
+  conc = std::max(2, std::min(conc, 64));  // >= 2: a batch always runs in slots on their own streams
+  return run_jobs(jobs, init7s, conc);
 }
 
 sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* pose7, int32_t* idx_out,
                                  double* w_out, float* d2_out) {
   SICP_REQUIRE(pose7 && idx_out, "null argument");
   SICP_CHECK(validate(algo, src, tgt, opts));
+  SICP_CHECK(validate_pose7(pose7, "sicp_correspondences"));
   SICP_CUDA(cudaSetDevice(src->device));
-  SICP_CHECK(precompute_pair(algo, src, tgt, opts, current_stream(), 0));
   cudaStream_t st = current_stream();
-  LMConfig cfg = make_cfg(algo, *opts);
-  Workspace ws;
-  sicp_status rc = ws.alloc(src, tgt, cfg, opts->min_class_points, st);
-  if (rc != SICP_OK) { ws.release(); return rc; }
-  std::memset(ws.h_ctl, 0, sizeof(RegCtl));
-  std::memcpy(ws.h_ctl->pose, pose7, 56);
-  const size_t nslot_c = (size_t)src->nslots * cfg.kc, n_c = src->n * cfg.kc;
+  SICP_CUDA(src->wait_built(st));
+  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(precompute_pair(algo, src, tgt, opts, st, nullptr));
+  Job jb;
+  jb.algo = algo; jb.src = src; jb.tgt = tgt; jb.opts = opts; jb.cfg = make_cfg(algo, *opts); jb.st = st;
+  SICP_CHECK(scratch_slot(src, jb.cfg.kc, &jb.sl));
+  Slot* ws = jb.sl;
+  LMConfig& cfg = jb.cfg;
+  const size_t nslot_c = (size_t)src->nslots * cfg.kc;
   std::vector<int> h_corr(nslot_c); std::vector<float> h_d2(nslot_c); std::vector<double> h_w(nslot_c);
   std::vector<float4> h_spts(src->nslots), h_tpts(tgt->nslots);
-  auto body = [&]() -> sicp_status {
-    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
-    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, nullptr, st));
-    SICP_CUDA(cudaMemcpyAsync(h_corr.data(), ws.d_corr, sizeof(int) * nslot_c, cudaMemcpyDeviceToHost, st));
-    SICP_CUDA(cudaMemcpyAsync(h_d2.data(), ws.d_d2, sizeof(float) * nslot_c, cudaMemcpyDeviceToHost, st));
-    SICP_CUDA(cudaMemcpyAsync(h_w.data(), ws.d_w, sizeof(double) * nslot_c, cudaMemcpyDeviceToHost, st));
-    SICP_CUDA(cudaMemcpyAsync(h_spts.data(), src->d_pts, sizeof(float4) * src->nslots, cudaMemcpyDeviceToHost, st));
-    SICP_CUDA(cudaMemcpyAsync(h_tpts.data(), tgt->d_pts, sizeof(float4) * tgt->nslots, cudaMemcpyDeviceToHost, st));
-    SICP_CUDA(cudaStreamSynchronize(st));
-    return SICP_OK;
-  };
-  rc = body();
-  ws.release();
-  SICP_CHECK(rc);
-  (void)n_c;
+  SICP_CHECK(jb.start(pose7));
+  SICP_CHECK(launch_cross_knn(src, tgt, ws->d_ctl->pose, nullptr, jb.class_map(), cfg.kc, ws->d_corr, ws->d_d2, st));
+  SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws->d_ctl->pose, nullptr, ws->d_corr, ws->d_d2, ws->d_w, ws->d_gpt, ws->d_gnt, nullptr, st));
+  SICP_CUDA(cudaMemcpyAsync(h_corr.data(), ws->d_corr, sizeof(int) * nslot_c, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaMemcpyAsync(h_d2.data(), ws->d_d2, sizeof(float) * nslot_c, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaMemcpyAsync(h_w.data(), ws->d_w, sizeof(double) * nslot_c, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaMemcpyAsync(h_spts.data(), src->d_pts, sizeof(float4) * src->nslots, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaMemcpyAsync(h_tpts.data(), tgt->d_pts, sizeof(float4) * tgt->nslots, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaStreamSynchronize(st));
   for (int s = 0; s < src->nslots; s++) {
     int o; std::memcpy(&o, &h_spts[s].w, 4);
     if (o < 0) continue;
@@ -436,30 +534,30 @@ sicp_status sicp_evaluate(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp
                           const double* eval_pose7, double* cost, double* g6, double* H36) {
   SICP_REQUIRE(corr_pose7 && eval_pose7 && cost && g6 && H36, "null argument");
   SICP_CHECK(validate(algo, src, tgt, opts));
+  SICP_CHECK(validate_pose7(corr_pose7, "sicp_evaluate (corr_pose7)"));
+  SICP_CHECK(validate_pose7(eval_pose7, "sicp_evaluate (eval_pose7)"));
   SICP_CUDA(cudaSetDevice(src->device));
-  SICP_CHECK(precompute_pair(algo, src, tgt, opts, current_stream(), 0));
   cudaStream_t st = current_stream();
-  LMConfig cfg = make_cfg(algo, *opts);
-  Workspace ws;
-  sicp_status rc = ws.alloc(src, tgt, cfg, opts->min_class_points, st);
-  if (rc != SICP_OK) { ws.release(); return rc; }
-  std::memset(ws.h_ctl, 0, sizeof(RegCtl));
-  std::memcpy(ws.h_ctl->pose, corr_pose7, 56);
-  std::memcpy(ws.h_ctl->pass_pose[0], eval_pose7, 56);  // scratch slot for the evaluation pose
-  double h_out[28];
-  auto body = [&]() -> sicp_status {
-    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
-    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, ws.d_map, cfg.kc, ws.d_corr, ws.d_d2, st));
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws.d_ctl->pose, nullptr, ws.d_corr, ws.d_d2, ws.d_w, ws.d_gpt, ws.d_gnt, nullptr, st));
-    double* d_out = &ws.d_ctl->pass_pose[8][0];
-    SICP_CHECK(launch_evaluate(src, cfg, ws.d_w, ws.d_gpt, ws.d_gnt, &ws.d_ctl->pass_pose[0][0], d_out, ws.d_partials, ws.grid, st));
-    SICP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost, st));
-    SICP_CUDA(cudaStreamSynchronize(st));
-    return SICP_OK;
-  };
-  rc = body();
-  ws.release();
-  SICP_CHECK(rc);
+  SICP_CUDA(src->wait_built(st));
+  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(precompute_pair(algo, src, tgt, opts, st, nullptr));
+  Job jb;
+  jb.algo = algo; jb.src = src; jb.tgt = tgt; jb.opts = opts; jb.cfg = make_cfg(algo, *opts); jb.st = st;
+  SICP_CHECK(scratch_slot(src, jb.cfg.kc, &jb.sl));
+  Slot* ws = jb.sl;
+  LMConfig& cfg = jb.cfg;
+  SICP_CHECK(jb.stage_class_map());
+  std::memset(ws->h_ctl, 0, sizeof(RegCtl));
+  std::memcpy(ws->h_ctl->pose, corr_pose7, 56);
+  std::memcpy(ws->h_ctl->pass_pose[0], eval_pose7, 56);  // scratch row for the evaluation pose
+  SICP_CUDA(cudaMemcpyAsync(ws->d_ctl, ws->h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+  SICP_CHECK(launch_cross_knn(src, tgt, ws->d_ctl->pose, nullptr, jb.class_map(), cfg.kc, ws->d_corr, ws->d_d2, st));
+  SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws->d_ctl->pose, nullptr, ws->d_corr, ws->d_d2, ws->d_w, ws->d_gpt, ws->d_gnt, nullptr, st));
+  double* d_out = &ws->d_ctl->pass_pose[8][0];
+  SICP_CHECK(launch_evaluate(src, cfg, ws->d_w, ws->d_gpt, ws->d_gnt, &ws->d_ctl->pass_pose[0][0], d_out, ws->d_partials, lm_grid_blocks(src->device), st));
+  double* h_out = &ws->h_ctl->pass_pose[8][0];  // pinned
+  SICP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * 28, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaStreamSynchronize(st));
   *cost = h_out[27];
   for (int a = 0; a < 6; a++) {
     g6[a] = h_out[21 + a];
@@ -471,28 +569,28 @@ sicp_status sicp_evaluate(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp
 sicp_status sicp_fused_labels(sicp_cloud* src, sicp_cloud* tgt, const sicp_options* opts, const double* pose7, uint32_t* labels_out) {
   SICP_REQUIRE(pose7 && labels_out, "null argument");
   SICP_CHECK(validate(SICP_ALGO_EM, src, tgt, opts));
+  SICP_CHECK(validate_pose7(pose7, "sicp_fused_labels"));
   SICP_CUDA(cudaSetDevice(src->device));
-  SICP_CHECK(precompute_pair(SICP_ALGO_EM, src, tgt, opts, current_stream(), 0));
   cudaStream_t st = current_stream();
-  LMConfig cfg = make_cfg(SICP_ALGO_EM, *opts);
-  Workspace ws;
-  sicp_status rc = ws.alloc(src, tgt, cfg, 0, st);
-  if (rc != SICP_OK) { ws.release(); return rc; }
-  std::memset(ws.h_ctl, 0, sizeof(RegCtl));
-  std::memcpy(ws.h_ctl->pose, pose7, 56);
+  SICP_CUDA(src->wait_built(st));
+  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(precompute_pair(SICP_ALGO_EM, src, tgt, opts, st, nullptr));
+  Job jb;
+  jb.algo = SICP_ALGO_EM; jb.src = src; jb.tgt = tgt; jb.opts = opts; jb.cfg = make_cfg(SICP_ALGO_EM, *opts); jb.st = st;
+  SICP_CHECK(scratch_slot(src, 4, &jb.sl));
+  Slot* ws = jb.sl;
+  SICP_CHECK(jb.start(pose7));
   uint32_t* d_lab = nullptr;
   auto body = [&]() -> sicp_status {
     SICP_CUDA(cudaMallocAsync(&d_lab, sizeof(uint32_t) * std::max<size_t>(1, src->n), st));
-    SICP_CUDA(cudaMemcpyAsync(ws.d_ctl, ws.h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
-    SICP_CHECK(launch_cross_knn(src, tgt, ws.d_ctl->pose, nullptr, nullptr, 4, ws.d_corr, ws.d_d2, st));
-    SICP_CHECK(launch_fused_labels(src, tgt, opts->epsilon, opts->gate_d2, ws.d_ctl->pose, ws.d_corr, ws.d_d2, d_lab, st));
+    SICP_CHECK(launch_cross_knn(src, tgt, ws->d_ctl->pose, nullptr, nullptr, 4, ws->d_corr, ws->d_d2, st));
+    SICP_CHECK(launch_fused_labels(src, tgt, opts->epsilon, opts->gate_d2, ws->d_ctl->pose, ws->d_corr, ws->d_d2, d_lab, st));
     SICP_CUDA(cudaMemcpyAsync(labels_out, d_lab, sizeof(uint32_t) * src->n, cudaMemcpyDeviceToHost, st));
     SICP_CUDA(cudaStreamSynchronize(st));
     return SICP_OK;
   };
-  rc = body();
+  const sicp_status rc = body();
   if (d_lab) cudaFreeAsync(d_lab, st);
-  ws.release();
   return rc;
 }
 

@@ -126,8 +126,9 @@ class Scene:
             with np.errstate(divide="ignore", invalid="ignore"):
                 t1 = (lo - o) / dirs
                 t2 = (hi - o) / dirs
-            tmin = np.nanmax(np.minimum(t1, t2), axis=1)
-            tmax = np.nanmin(np.maximum(t1, t2), axis=1)
+            lo3, hi3 = np.minimum(t1, t2), np.maximum(t1, t2)  # NaN (0/0: ray parallel to a slab it starts on) is ignored, like nanmax/nanmin
+            tmin = np.fmax(np.fmax(lo3[:, 0], lo3[:, 1]), lo3[:, 2])
+            tmax = np.fmin(np.fmin(hi3[:, 0], hi3[:, 1]), hi3[:, 2])
             ok = (tmax >= tmin) & (tmin > 1e-6) & (tmin < best)
             best = np.where(ok, tmin, best)
             cls = np.where(ok, c, cls)
@@ -208,6 +209,36 @@ def lidar_scan(rng, scene, sensor_R, sensor_t, n_points, max_range=80.0, sigma=0
     pts = np.concatenate(pts)[:n_points]
     cls = np.concatenate(cls)[:n_points]
     return pts.astype(np.float32), cls.astype(np.int64)
+
+
+def cached(name, *args, **kw):
+    """Disk cache of a generator call (identical output, keyed by name + arguments): synthetic scans take seconds each on
+    the host, and bench.py / tools generate the same seeded pairs again and again.  SICP_SYNTH_CACHE=0 disables it."""
+    import hashlib
+    import os
+    import pickle
+
+    root = os.environ.get("SICP_SYNTH_CACHE", "/tmp/sicp_synth_cache")
+    fn = globals()[name]
+    if root in ("", "0"):
+        return fn(*args, **kw)
+    key = hashlib.sha1(repr((name, args, sorted(kw.items()))).encode()).hexdigest()[:20]
+    path = os.path.join(root, f"{name}_{key}.pkl")
+    try:
+        with open(path, "rb") as f:
+            return pickle.load(f)
+    except Exception:
+        pass
+    out = fn(*args, **kw)
+    try:
+        os.makedirs(root, exist_ok=True)
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:
+            pickle.dump(out, f, protocol=4)
+        os.replace(tmp, path)
+    except Exception:
+        pass
+    return out
 
 
 def _yaw(psi):

@@ -37,6 +37,19 @@ def main():
     assert (lo, hi) == pkg.shard.shard_range(n_pairs, rank, world)
     back = pkg.shard.from_records(rec)
     assert back[-1]["outer_iter"] == 3 + (n_pairs - 1) % 5
+    # interleaved assignment: unit i -> rank i mod world, gathered back into global pair order
+    ids = pkg.shard.shard_ids(n_pairs, rank, world, "interleaved")
+    local = pkg.shard.to_records([fake_result(p, j) for p in ids for j in range(inits)]) if ids else np.zeros((0, pkg.shard.RECORD))
+    rec2 = pkg.shard.gather_by_id(ids, local, n_pairs, per_unit=inits)
+    assert np.array_equal(rec2, exp), "interleaved gather differs from the single-process result"
+    # dynamic chunks: one shared atomic counter in the c10d store; every pair is claimed exactly once
+    from torch.distributed.distributed_c10d import _get_default_store
+
+    dc = pkg.shard.DynamicChunks(_get_default_store(), n_pairs, chunk=2, key="test_chunks")
+    mine = [p for lo2, hi2 in dc for p in range(lo2, hi2)]
+    local = pkg.shard.to_records([fake_result(p, j) for p in mine for j in range(inits)]) if mine else np.zeros((0, pkg.shard.RECORD))
+    rec3 = pkg.shard.gather_by_id(mine, local, n_pairs, per_unit=inits)
+    assert np.array_equal(rec3, exp), "dynamic-chunk gather differs from the single-process result"
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank}/{world} ok pairs [{lo},{hi})")

@@ -26,6 +26,20 @@ def test_shard_ranges_cover_everything(pkg):
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_interleaved_and_dynamic_assignment(pkg):
+    for n in (0, 1, 7, 64):
+        for world in (1, 2, 3, 8):
+            ids = [pkg.shard.shard_ids(n, r, world, "interleaved") for r in range(world)]
+            assert sorted(i for b in ids for i in b) == list(range(n))
+            assert max(len(b) for b in ids) - min(len(b) for b in ids) <= 1
+            assert [i for r in range(world) for i in pkg.shard.shard_ids(n, r, world, "block")] == list(range(n))
+    dc = pkg.shard.DynamicChunks(None, 11, 4)  # single process: a local counter
+    assert list(dc) == [(0, 4), (4, 8), (8, 11)] and dc.claimed == [(0, 4), (4, 8), (8, 11)]
+    res = [dict(pose=np.arange(7.0) + i, outer_iter=i, lm_iters_total=i, final_cost=0.0, n_corr_last=0, flags=0) for i in (2, 0, 1)]
+    rec = pkg.shard.gather_by_id([2, 0, 1], pkg.shard.to_records(res), 3)
+    assert [int(r[7]) for r in rec] == [0, 1, 2]
+
+
 def test_records_round_trip(pkg):
     res = [dict(pose=np.arange(7) + i, outer_iter=i, lm_iters_total=10 * i, final_cost=0.5 * i, n_corr_last=i * i, flags=i & 1) for i in range(5)]
     rec = pkg.shard.to_records(res)

@@ -5,7 +5,7 @@ import numpy as np
 import semantic_icp_b200 as pkg
 sicp, synth = pkg.sicp, pkg.synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-pairs = [synth.kitti_pair(i) for i in range(B)]
+pairs = [synth.cached("kitti_pair", i) for i in range(B)]
 p = pairs[0]
 opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
 inits = np.stack([q["init"] for q in pairs])

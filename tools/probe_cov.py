@@ -3,7 +3,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import semantic_icp_b200 as pkg
 sicp, synth = pkg.sicp, pkg.synth
-p = synth.kitti_pair(0)
+p = synth.cached("kitti_pair", 0)
 best = {}
 for rep in range(5):
     s, t = sicp.Cloud(p["src_xyz"], p["src_labels"]), sicp.Cloud(p["tgt_xyz"], p["tgt_labels"])

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import semantic_icp_b200 as pkg
 sicp, synth = pkg.sicp, pkg.synth
-sicp.LIB_PATH = os.path.join(pkg.PKG_ROOT, "lib", "libsicp_b200_stats.so")
+sicp.LIB_PATH = os.environ.get("SICP_STATS_LIB") or os.path.join(pkg.PKG_ROOT, "lib", "libsicp_b200_stats.so")
 L = sicp.lib()
 def stats(reset=True):
     out = (C.c_ulonglong * 8)()

@@ -6,7 +6,7 @@ import semantic_icp_b200 as pkg
 sicp, synth = pkg.sicp, pkg.synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 conc = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-pairs = [synth.kitti_pair(i) for i in range(B)]
+pairs = [synth.cached("kitti_pair", i) for i in range(B)]
 p = pairs[0]
 inits = np.stack([q["init"] for q in pairs])
 path = "/tmp/sicp_trace.txt"
