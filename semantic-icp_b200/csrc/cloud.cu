@@ -174,10 +174,8 @@ __global__ void transform_f32_kernel(const float4* __restrict__ pts, int nslots,
 // -------------------------------------------------------------------------------------------------------------
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// Everything here is enqueued on `st`; the function does not wait for the device.
-static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t* d_labels, const uint8_t* d_rank,
-                               const std::vector<int>& class_sizes, cudaStream_t st) {
-  const int n = (int)c->n;
+// Host-side layout of the search structure (segments, slots, leaves, nodes): final as soon as the class sizes are known.
+static void layout_cloud(sicp_cloud* c, const std::vector<int>& class_sizes) {
   const int nseg = (int)class_sizes.size();
   c->nseg = nseg;
   c->h_seg.assign(nseg, Segment());
@@ -197,6 +195,12 @@ static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t
     start += sg.n; p0 += sg.nleaf * kLeaf; leaf0 += sg.nleaf;
   }
   c->nslots = p0; c->nleaf = leaf0; c->nnodes = node0;
+}
+
+// Device side of the build.  Everything here is enqueued on `st`; the function does not wait for the device.
+static sicp_status build_cloud(sicp_cloud* c, const float* d_xyz, const uint32_t* d_labels, const uint8_t* d_rank, cudaStream_t st) {
+  const int n = (int)c->n;
+  const int nseg = c->nseg;
 
   // one persistent slab: pts | label | seg_of_leaf | seg | node_lo | node_hi | slot_of_orig | bb
   size_t off = 0;
@@ -384,7 +388,9 @@ uint64_t sicp_launch_count(void) { return g_launches; }
 sicp_status sicp_set_stream(void* s) { g_stream = (cudaStream_t)s; return SICP_OK; }
 
 // h_labels (nullable) are the caller's labels, label_stride bytes apart, when they live on the host.
-static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, const void* h_labels, size_t label_stride, size_t n, int layout,
+// d_xyz / d_labels are staging buffers OWNED by this call (allocated stream-ordered on the current stream): they are
+// freed after an eager build, or kept by the cloud until its deferred build.
+static sicp_status create_common(float* d_xyz, uint32_t* d_labels, const void* h_labels, size_t label_stride, size_t n, int layout,
                                  int device, sicp_cloud** out) {
   cudaStream_t st = current_stream();
   sicp_cloud* c = new sicp_cloud();
@@ -399,15 +405,55 @@ static sicp_status create_common(const float* d_xyz, const uint32_t* d_labels, c
     for (size_t i = 0; i < n; i++) { uint32_t l; std::memcpy(&l, (const char*)h_labels + i * label_stride, 4); lo = std::min(lo, l); hi = std::max(hi, l); }
     c->min_label = lo; c->max_label = hi; c->label_range_known = true;
   }
-  if (rc == SICP_OK) rc = build_cloud(c, d_xyz, d_labels, d_rank, sizes, st);
-  if (d_rank) cudaFreeAsync(d_rank, st);
-  if (rc == SICP_OK && (cudaEventCreateWithFlags(&c->built_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(c->built_ev, st) != cudaSuccess)) {
-    set_error("event creation failed"); rc = SICP_ERR_CUDA;
+  if (rc == SICP_OK) layout_cloud(c, sizes);
+  static const bool eager = [] { const char* e = getenv("SICP_EAGER_BUILD"); return e && *e && *e != '0'; }();
+  if (rc == SICP_OK && cudaEventCreateWithFlags(&c->built_ev, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = SICP_ERR_CUDA; }
+  if (rc == SICP_OK && layout == SICP_CLOUD_WHOLE && !eager && n > 0) {
+    // deferred: keep the staged inputs, build on the first consumer's stream (ensure_built)
+    if (cudaEventCreateWithFlags(&c->staged_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(c->staged_ev, st) != cudaSuccess) {
+      set_error("event creation failed"); rc = SICP_ERR_CUDA;
+    } else {
+      c->stage_xyz = d_xyz; c->stage_lab = d_labels; c->pending_build = true;
+      d_xyz = nullptr; d_labels = nullptr;
+    }
+  } else if (rc == SICP_OK) {
+    rc = build_cloud(c, d_xyz, d_labels, d_rank, st);
+    if (rc == SICP_OK && cudaEventRecord(c->built_ev, st) != cudaSuccess) { set_error("event record failed"); rc = SICP_ERR_CUDA; }
   }
+  if (d_rank) cudaFreeAsync(d_rank, st);
+  if (d_xyz) cudaFreeAsync(d_xyz, st);
+  if (d_labels) cudaFreeAsync(d_labels, st);
   if (rc != SICP_OK) { sicp_cloud_destroy(c); return rc; }
   *out = c;
   return SICP_OK;
 }
+
+}  // extern "C"
+
+sicp_status sicp::ensure_built(const sicp_cloud* cc, cudaStream_t st) {
+  sicp_cloud* c = const_cast<sicp_cloud*>(cc);
+  std::lock_guard<std::mutex> lk(c->build_mu);
+  if (c->pending_build) {
+    SICP_CUDA(cudaSetDevice(c->device));
+    SICP_CUDA(cudaStreamWaitEvent(st, c->staged_ev, 0));
+    SICP_CHECK(build_cloud(c, c->stage_xyz, c->stage_lab, nullptr, st));
+    SICP_CUDA(cudaFreeAsync(c->stage_xyz, st));
+    if (c->stage_lab) SICP_CUDA(cudaFreeAsync(c->stage_lab, st));
+    c->stage_xyz = nullptr; c->stage_lab = nullptr;
+    SICP_CUDA(cudaEventRecord(c->built_ev, st));
+    c->pending_build = false;
+    return SICP_OK;
+  }
+  if (c->built_ev) SICP_CUDA(cudaStreamWaitEvent(st, c->built_ev, 0));
+  return SICP_OK;
+}
+sicp_status sicp::ensure_ready(const sicp_cloud* c, cudaStream_t st) {
+  SICP_CHECK(ensure_built(c, st));
+  if (c->ready_ev) SICP_CUDA(cudaStreamWaitEvent(st, c->ready_ev, 0));
+  return SICP_OK;
+}
+
+extern "C" {
 
 sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* labels, size_t label_stride, size_t n, int layout,
                               int device, sicp_cloud** out) {
@@ -432,10 +478,7 @@ sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* la
       else SICP_CUDA(cudaMemcpy2DAsync(d_lab, 4, labels, label_stride, 4, n, cudaMemcpyHostToDevice, st));
     }
   }
-  sicp_status rc = create_common(d_xyz, d_lab, labels, label_stride, n, layout, device, out);
-  cudaFreeAsync(d_xyz, st);
-  if (d_lab) cudaFreeAsync(d_lab, st);
-  return rc;
+  return create_common(d_xyz, d_lab, labels, label_stride, n, layout, device, out);  // takes the staging buffers over
 }
 
 sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_labels, size_t n, int layout, int device, sicp_cloud** out) {
@@ -445,17 +488,27 @@ sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_label
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || layout == SICP_CLOUD_PER_CLASS, "bad layout");
   SICP_REQUIRE(layout == SICP_CLOUD_WHOLE || d_labels, "PER_CLASS layout needs labels");
   SICP_CHECK(init_device(device));
-  return create_common(d_xyz, d_labels, nullptr, 4, n, layout, device, out);
+  // the caller's buffers are only read during this call: stage owned copies (device to device) for the (possibly deferred) build
+  cudaStream_t st = current_stream();
+  float* s_xyz = nullptr; uint32_t* s_lab = nullptr;
+  SICP_CUDA(cudaMallocAsync(&s_xyz, std::max<size_t>(1, n) * 12, st));
+  if (n) SICP_CUDA(cudaMemcpyAsync(s_xyz, d_xyz, 12 * n, cudaMemcpyDeviceToDevice, st));
+  if (d_labels) {
+    SICP_CUDA(cudaMallocAsync(&s_lab, std::max<size_t>(1, n) * 4, st));
+    if (n) SICP_CUDA(cudaMemcpyAsync(s_lab, d_labels, 4 * n, cudaMemcpyDeviceToDevice, st));
+  }
+  return create_common(s_xyz, s_lab, nullptr, 4, n, layout, device, out);
 }
 
 void sicp_cloud_destroy(sicp_cloud* c) {
   if (!c) return;
   cudaStream_t st = current_stream();
   cudaSetDevice(c->device);
-  void* bufs[] = {c->d_slab, c->d_nrm, c->d_avec};
+  void* bufs[] = {c->d_slab, c->d_nrm, c->d_avec, c->stage_xyz, c->stage_lab};
   for (void* b : bufs) if (b) cudaFreeAsync(b, st);
   if (c->ready_ev) cudaEventDestroy(c->ready_ev);
   if (c->built_ev) cudaEventDestroy(c->built_ev);
+  if (c->staged_ev) cudaEventDestroy(c->staged_ev);
   delete c;
 }
 
@@ -485,7 +538,7 @@ sicp_status sicp_cloud_transform_f32(const sicp_cloud* c, const double* pose7, v
   cudaStream_t st = current_stream();
   SICP_CUDA(cudaSetDevice(c->device));
   if (c->n == 0) return SICP_OK;
-  SICP_CUDA(c->wait_built(st));
+  SICP_CHECK(ensure_built(c, st));
   double Rd[9];
   quat_to_R(pose7, Rd);
   Mat34f M;

@@ -116,13 +116,21 @@ struct sicp_cloud {
   cudaEvent_t ready_ev = nullptr;  // recorded after the last precompute; consumers on other streams wait on it
   cudaEvent_t built_ev = nullptr;  // recorded after the build (upload, sort, tree); work on other streams waits on it
   std::mutex mu;                   // guards the precompute cache (pairs of an odometry chain share clouds across host threads)
+  // Deferred build: the sort / tree build of a WHOLE cloud runs on the stream of its FIRST consumer (sicp::ensure_built), so
+  // that the builds of a batch overlap the registrations already in flight instead of all preceding them on the creating
+  // stream.  Until then the inputs live in owned staging buffers; the host-side layout (nslots, nleaf ...) is final at once.
+  bool pending_build = false;
+  float* stage_xyz = nullptr;
+  uint32_t* stage_lab = nullptr;
+  cudaEvent_t staged_ev = nullptr;  // recorded on the creating stream after the staging copies
+  std::mutex build_mu;
   sicp::CloudView view() const;
-  // Every entry point that reads the cloud on stream `st` calls these first (a wait on a completed event costs nothing):
-  // the cloud may have been built / precomputed on another stream or by another host thread.
-  cudaError_t wait_built(cudaStream_t st) const { return built_ev ? cudaStreamWaitEvent(st, built_ev, 0) : cudaSuccess; }
-  cudaError_t wait_ready(cudaStream_t st) const {
-    cudaError_t e = wait_built(st);
-    if (e == cudaSuccess && ready_ev) e = cudaStreamWaitEvent(st, ready_ev, 0);
-    return e;
-  }
 };
+
+namespace sicp {
+// Every entry point that reads a cloud on stream `st` calls one of these first: the cloud may still have to be built
+// (deferred build), or was built / precomputed on another stream or by another host thread (a wait on a completed event
+// costs nothing).  ensure_ready also waits for the last covariance precompute.
+sicp_status ensure_built(const sicp_cloud* c, cudaStream_t st);
+sicp_status ensure_ready(const sicp_cloud* c, cudaStream_t st);
+}  // namespace sicp

@@ -150,8 +150,8 @@ __device__ __forceinline__ int home_leaf(const CloudView& tv, const Segment& sg,
 // HOME leaf (Morton binary search) and the distinct home leaves of the packet (+- SEED Morton neighbours) are pushed on
 // top of the stack: they are scanned first, after which every lane's k-th bound is already close to final.  Seed leaves
 // are remembered (one per lane register) and skipped when the traversal reaches them again.
-template <int K>
-__device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& sg, float qx, float qy, float qz, bool valid, TopK<K>& L,
+template <int K, class ListT>
+__device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& sg, float qx, float qy, float qz, bool valid, ListT& L,
                                            WarpScratch& ws) {
   if (sg.nleaf == 0) return;
   const int lane = threadIdx.x & 31;

@@ -119,6 +119,31 @@ __device__ __forceinline__ void svd3_normal(const double* A, double* normal) {
 }
 
 // ------------------------------------------------------------------ K1: self kNN + PCA
+// moments in kNN order (impl/gicp.hpp:198-222): float*float products rounded to float, double sums, divisor k
+struct Moments {
+  double mean[3] = {0, 0, 0};
+  double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
+  __device__ __forceinline__ void add(const float4& p) {
+    mean[0] += p.x; mean[1] += p.y; mean[2] += p.z;
+    c00 += __fmul_rn(p.x, p.x);
+    c10 += __fmul_rn(p.y, p.x); c11 += __fmul_rn(p.y, p.y);
+    c20 += __fmul_rn(p.z, p.x); c21 += __fmul_rn(p.z, p.y); c22 += __fmul_rn(p.z, p.z);
+  }
+  __device__ __forceinline__ void normal(int k, double* nv) {
+    const double kd = (double)k;
+    mean[0] /= kd; mean[1] /= kd; mean[2] /= kd;
+    double A[9];
+    c00 /= kd; c00 -= mean[0] * mean[0];
+    c10 /= kd; c10 -= mean[1] * mean[0];
+    c11 /= kd; c11 -= mean[1] * mean[1];
+    c20 /= kd; c20 -= mean[2] * mean[0];
+    c21 /= kd; c21 -= mean[2] * mean[1];
+    c22 /= kd; c22 -= mean[2] * mean[2];
+    A[0] = c00; A[1] = c10; A[2] = c20; A[3] = c10; A[4] = c11; A[5] = c21; A[6] = c20; A[7] = c21; A[8] = c22;
+    svd3_normal(A, nv);
+  }
+};
+
 template <int K>
 __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, const int* __restrict__ slot_of_orig, int k, double* __restrict__ nrm,
                                                                 int* __restrict__ selfnn, uint8_t* __restrict__ nbr_label) {
@@ -138,37 +163,18 @@ __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, co
   L.init();
   knn_search<K>(cv, sg, me.x, me.y, me.z, valid, L, s_ws[wib]);
   if (!valid) return;
-  // moments in kNN order (impl/gicp.hpp:198-222): float*float products rounded to float, double sums, divisor k
-  double mean[3] = {0, 0, 0};
-  double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
+  Moments mo;
 #pragma unroll
   for (int j = 0; j < K; j++) {
     const int nslot = (j < k && L.orig(j) >= 0) ? slot_of_orig[L.orig(j)] : -1;
-    if (nslot >= 0) {
-      const float4 p = cv.pts[nslot];
-      mean[0] += p.x; mean[1] += p.y; mean[2] += p.z;
-      c00 += __fmul_rn(p.x, p.x);
-      c10 += __fmul_rn(p.y, p.x); c11 += __fmul_rn(p.y, p.y);
-      c20 += __fmul_rn(p.z, p.x); c21 += __fmul_rn(p.z, p.y); c22 += __fmul_rn(p.z, p.z);
+    if (nslot >= 0) mo.add(cv.pts[nslot]);
+    if (j < k) {
       if (selfnn) selfnn[(size_t)slot * k + j] = nslot;
-      if (nbr_label) nbr_label[(size_t)slot * kMaxK + j] = (uint8_t)cv.label[nslot];
-    } else if (j < k) {
-      if (selfnn) selfnn[(size_t)slot * k + j] = -1;
-      if (nbr_label) nbr_label[(size_t)slot * kMaxK + j] = 0;
+      if (nbr_label) nbr_label[(size_t)slot * kMaxK + j] = nslot >= 0 ? (uint8_t)cv.label[nslot] : 0;
     }
   }
-  const double kd = (double)k;
-  mean[0] /= kd; mean[1] /= kd; mean[2] /= kd;
-  double A[9];
-  c00 /= kd; c00 -= mean[0] * mean[0];
-  c10 /= kd; c10 -= mean[1] * mean[0];
-  c11 /= kd; c11 -= mean[1] * mean[1];
-  c20 /= kd; c20 -= mean[2] * mean[0];
-  c21 /= kd; c21 -= mean[2] * mean[1];
-  c22 /= kd; c22 -= mean[2] * mean[2];
-  A[0] = c00; A[1] = c10; A[2] = c20; A[3] = c10; A[4] = c11; A[5] = c21; A[6] = c20; A[7] = c21; A[8] = c22;
   double nv[3];
-  svd3_normal(A, nv);
+  mo.normal(k, nv);
   nrm[slot] = nv[0];
   nrm[(size_t)cv.nslots + slot] = nv[1];
   nrm[2 * (size_t)cv.nslots + slot] = nv[2];
@@ -392,7 +398,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
     return SICP_OK;
   cudaStream_t st = current_stream();
   SICP_CUDA(cudaSetDevice(c->device));
-  SICP_CUDA(c->wait_built(st));
+  SICP_CHECK(ensure_built(c, st));
   if (c->d_nrm || c->d_avec) {
     // Re-precompute with other parameters (rare): registrations on other streams may still be reading the old normals /
     // label vectors, so drain the device before they are overwritten or freed.
@@ -443,7 +449,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
 
 static sicp_status download_rows(const sicp_cloud* c, const double* d_in, int cols, int soa, double* out) {
   cudaStream_t st = current_stream();
-  SICP_CUDA(c->wait_ready(st));
+  SICP_CHECK(ensure_ready(c, st));
   double* d_tmp;
   SICP_CUDA(cudaMallocAsync(&d_tmp, sizeof(double) * cols * std::max<size_t>(1, c->n), st));
   if (c->nslots) unsort_rows_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->view(), d_in, cols, soa, d_tmp);
@@ -464,7 +470,7 @@ sicp_status sicp_cloud_get_covariances(const sicp_cloud* c, double* out) {
   if (!c->pre_valid) { set_error("precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(c->wait_ready(st));
+  SICP_CHECK(ensure_ready(c, st));
   double* d_tmp;
   SICP_CUDA(cudaMallocAsync(&d_tmp, sizeof(double) * 9 * std::max<size_t>(1, c->n), st));
   if (c->nslots) cov_rows_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->view(), c->pre_eps, d_tmp);
@@ -485,7 +491,7 @@ sicp_status sicp_cloud_get_label_distributions(const sicp_cloud* c, double* out)
   if (!c->pre_valid || c->pre_N == 0) { set_error("EM precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(c->wait_ready(st));
+  SICP_CHECK(ensure_ready(c, st));
   const int N = c->pre_N;
   uint8_t* d_nbr; double *d_cm, *d_dist, *d_a, *d_n;
   SICP_CUDA(cudaMallocAsync(&d_nbr, (size_t)kMaxK * std::max(1, c->nslots), st));
@@ -506,7 +512,7 @@ sicp_status sicp_cloud_get_self_neighbours(const sicp_cloud* c, int32_t* out) {
   if (!c->pre_valid) { set_error("precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(c->wait_ready(st));
+  SICP_CHECK(ensure_ready(c, st));
   const int k = c->pre_k;
   int* d_nn; int32_t* d_out; double* d_n;
   SICP_CUDA(cudaMallocAsync(&d_nn, sizeof(int) * k * std::max(1, c->nslots), st));
@@ -527,8 +533,8 @@ sicp_status sicp_knn_cloud(const sicp_cloud* tgt, const sicp_cloud* q, const dou
   SICP_CHECK(validate_pose7(pose7, "sicp_knn_cloud", true));
   SICP_CUDA(cudaSetDevice(tgt->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(tgt->wait_built(st));
-  SICP_CUDA(q->wait_built(st));
+  SICP_CHECK(ensure_built(tgt, st));
+  SICP_CHECK(ensure_built(q, st));
   int* d_map = nullptr;
   SICP_CHECK(make_class_map(q, tgt, -1, &d_map, st));
   double* d_pose = nullptr;

@@ -54,11 +54,23 @@ __device__ __forceinline__ double det_S(const double* u, const double* v, double
   return 2.0 * (a - be) * (a + be);
 }
 
+// GICPCostFunction::Probability converted to bool (gicp_cost_function.h:75-87): is
+//   density = pow(det(2 pi S), -1/2) * exp(mahal)
+// exactly zero in the reference's arithmetic?  exp() is rounded to a double first — into the DENORMAL range when mahal is
+// in (-745.13, -708.4) — and the product is rounded again, so the answer near the bottom of the range depends on both
+// roundings.  Device exp() is not trusted there: the first rounding is redone in integer units of the smallest denormal
+// (2^-1074; rint = round-half-even like the hardware), the second is the comparison with half a unit.  Callers only get
+// here for mahal <= -700; above that the density is a normal number times >= 0.022 and cannot vanish.
+__device__ __forceinline__ bool density_is_zero(double det2pi, double mahal) {
+  const double p = pow(det2pi, -0.5);
+  const double units = rint(exp(mahal + 744.4400719213812623));  // exp(mahal) / 2^-1074, rounded as the reference's exp rounds it
+  return p * units <= 0.5;                                        // false for NaN: a NaN density converts to `true`
+}
+
 // ------------------------------------------------------------------ K3: E-step
-// Besides the weights it GATHERS the target point and normal of every candidate pair into residual-ordered arrays, so
-// that the many LM sweeps of the pass stream them with coalesced loads instead of repeating the gather.  Gathered
-// arrays are c-major: record (slot, c) lives at c * nslots + slot, so a sweep thread that owns one source slot reads
-// each of its kc records with a fully coalesced warp access.
+// Besides the weights it GATHERS the target point and normal of every candidate pair, and copies the source point and
+// normal, into the group blocks of kernels.h (struct Rec), so that the many LM sweeps of the pass stream them with one
+// bulk copy per 32 slots instead of repeating the gather.
 // One thread per SOURCE SLOT and its KC candidates: the source row a_s, the source point/normal and the rotated
 // normal are fetched / computed once per slot, and the KC independent gathers of the target rows a_t are in flight
 // together (16-byte loads when the row is 16-byte aligned), which is what hides the gather latency — this kernel
@@ -68,13 +80,11 @@ template <int KC>
 __global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, CloudView tv, int algo, double eps, double gate_d2,
                                                               const double* __restrict__ pose7, const int* __restrict__ stop,
                                                               int* __restrict__ corr, const float* __restrict__ d2,
-                                                              double* __restrict__ wout, float4* __restrict__ g_pt,
-                                                              double* __restrict__ g_nt, RegCtl* ctl) {
+                                                              char* __restrict__ rec, RegCtl* ctl) {
   if (stop && *stop) return;
   const long long gs = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = gs < sv.nslots;
   const int slot = live ? (int)gs : 0;
-  const size_t nslots = (size_t)sv.nslots, ncorr = nslots * KC;
   int ts[KC];
   double w[KC];
 #pragma unroll
@@ -94,6 +104,8 @@ __global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, Clou
     nt[c][0] = __ldg(&tv.nrm[t]); nt[c][1] = __ldg(&tv.nrm[(size_t)tv.nslots + t]); nt[c][2] = __ldg(&tv.nrm[2 * (size_t)tv.nslots + t]);
     if (ts[c] >= 0) w[c] = 1.0;
   }
+  double ps[3], ns[3];
+  load_point(sv, slot, ps, ns);
   if (algo == SICP_ALGO_EM) {
     // label compatibility (em_icp.hpp:84-89) with a_p = CM^T dist_p precomputed per point: w = a_t . a_s, summed in
     // ascending class order
@@ -125,8 +137,7 @@ __global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, Clou
     RT P;
     quat_to_R(pose7, P.R);
     P.t[0] = pose7[4]; P.t[1] = pose7[5]; P.t[2] = pose7[6];
-    double ps[3], ns[3], m[3], q[3];
-    load_point(sv, slot, ps, ns);
+    double m[3], q[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       m[i] = P.R[3 * i] * ns[0] + P.R[3 * i + 1] * ns[1] + P.R[3 * i + 2] * ns[2];
@@ -146,24 +157,38 @@ __global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, Clou
       if (!(mahal > -700.0)) {
         const double two_pi = 6.283185307179586;
         const double det2pi = (two_pi * two_pi * two_pi) * det_S(nt[c], m, kappa);
-        const double density = pow(det2pi, -0.5) * exp(mahal);
-        if (density == 0.0) prob[c] *= 0.0;  // NaN stays "true" like the bool conversion
+        if (density_is_zero(det2pi, mahal)) prob[c] *= 0.0;  // NaN stays "true" like the bool conversion
       }
       w[c] = prob[c];
     }
   }
   int kept = 0;
   if (live) {
+    char* blk = rec + (size_t)(slot >> 5) * Rec::group_bytes(KC);
+    const int lane = slot & 31;
 #pragma unroll
     for (int c = 0; c < KC; c++) {
-      const size_t ro = (size_t)c * nslots + slot;  // gathered arrays are c-major
+      char* cb = blk + c * Rec::kCandBytes;
       const bool ok = ts[c] >= 0;
       kept += ok;
-      wout[ro] = w[c];
+      reinterpret_cast<double*>(cb + Rec::kW)[lane] = w[c];
       // no residual: zeroed geometry keeps the branch-free sweep finite (its weight is 0)
-      g_pt[ro] = ok ? make_float4(tp[c].x, tp[c].y, tp[c].z, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
-      g_nt[ro] = ok ? nt[c][0] : 0.0; g_nt[ncorr + ro] = ok ? nt[c][1] : 0.0; g_nt[2 * ncorr + ro] = ok ? nt[c][2] : 0.0;
+      reinterpret_cast<float*>(cb + Rec::kPx)[lane] = ok ? tp[c].x : 0.f;
+      reinterpret_cast<float*>(cb + Rec::kPy)[lane] = ok ? tp[c].y : 0.f;
+      reinterpret_cast<float*>(cb + Rec::kPz)[lane] = ok ? tp[c].z : 0.f;
+      reinterpret_cast<double*>(cb + Rec::kNx)[lane] = ok ? nt[c][0] : 0.0;
+      reinterpret_cast<double*>(cb + Rec::kNy)[lane] = ok ? nt[c][1] : 0.0;
+      reinterpret_cast<double*>(cb + Rec::kNz)[lane] = ok ? nt[c][2] : 0.0;
     }
+    // source side; padding slots (NaN coordinates, undefined normals) and slots without any residual are zeroed
+    char* sb = blk + KC * Rec::kCandBytes;
+    const bool any = kept > 0;
+    reinterpret_cast<float*>(sb + Rec::kSx)[lane] = any ? (float)ps[0] : 0.f;
+    reinterpret_cast<float*>(sb + Rec::kSy)[lane] = any ? (float)ps[1] : 0.f;
+    reinterpret_cast<float*>(sb + Rec::kSz)[lane] = any ? (float)ps[2] : 0.f;
+    reinterpret_cast<double*>(sb + Rec::kSnx)[lane] = any ? ns[0] : 0.0;
+    reinterpret_cast<double*>(sb + Rec::kSny)[lane] = any ? ns[1] : 0.0;
+    reinterpret_cast<double*>(sb + Rec::kSnz)[lane] = any ? ns[2] : 0.0;
   }
   if (ctl) {  // residual blocks of this pass (diagnostics)
     kept += __shfl_xor_sync(kFullMask, kept, 16); kept += __shfl_xor_sync(kFullMask, kept, 8); kept += __shfl_xor_sync(kFullMask, kept, 4);
@@ -471,9 +496,7 @@ static __device__ unsigned long long g_lm_blk[512][2];  // per block: cycles in 
 struct LMArgs {
   CloudView sv;
   LMConfig cfg;
-  const double* w;          // [kc][nslots] E-step weights (0 = no residual), c-major
-  const float4* g_pt;       // [kc][nslots] gathered target points
-  const double* g_nt;       // [3][kc][nslots] gathered target normals
+  const char* rec;          // group blocks of the pass (kernels.h: struct Rec)
   RegCtl* ctl;
   double* partials;         // [gridDim.x * kAcc]
   LMSync* sync;
@@ -512,16 +535,35 @@ __device__ __forceinline__ void loss_fast(double w, double res, double* rho0, do
   *rho1 = f1 * (0.5 * rs);
 }
 
-// w[i] with a runtime index, without sending the array to local memory
-template <int KC>
-__device__ __forceinline__ double pick_w(const double* w, int i) {
-  double r = w[0];
-#pragma unroll
-  for (int j = 1; j < KC; j++) r = (i == j) ? w[j] : r;
-  return r;
+// ---- bulk (TMA) copies global -> shared with mbarrier completion: one elected lane arms the barrier with the byte
+// count and issues the copy; every lane of the warp then waits on the barrier's phase parity
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic-proxy reads of the buffer are done
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
 }
 
-// Residual sweep at the pose (P.R, P.t): one thread owns one source slot and its KC gathered records.
+// Per-warp double buffer of group blocks.  `uses` counts the blocks consumed so far over the whole launch: use u lives in
+// buffer u & 1 and completes phase (u >> 1) & 1 of that buffer's barrier.
+struct GroupPipe {
+  char* buf;        // 2 * group_bytes of shared memory owned by this warp
+  unsigned bar;     // shared address of its two 8-byte barriers
+  unsigned uses;
+  bool primed;      // the copy for use `uses` is already in flight (issued at the end of the previous sweep)
+};
+
+// Residual sweep at the pose (P.R, P.t): one thread owns one source slot and its KC records.
 // Everything is evaluated in the TARGET frame so that no per-residual R^T products are needed:
 //   d = p_t - (R p_s + t),  m = R n_s,  b = (2I - kappa(n_t n_t^T + m m^T))^-1 d,  res = d.b
 //   local 6-dof Jacobian of res for T*exp(delta):  J = -2 D j,  j = [b ; v x b],  v = R p_s - kappa (m.b) m,
@@ -530,45 +572,37 @@ __device__ __forceinline__ double pick_w(const double* w, int i) {
 // (4, -2, 1/2) and the rotation D are applied ONCE to the 28 grid totals by the controller block.
 // The KC records of a slot are evaluated by straight-line, branch-free code (records without a residual have w = 0 and
 // zeroed geometry) so that their dependency chains interleave.
-// CH = records of a slot evaluated together (CH == KC: all of them, the widest interleave, needs ~240 registers;
-// CH < KC: the slot's records are taken CH at a time by a rolled loop, which fits 128 registers and twice the warps).
-template <int ALGO, int KC, int THREADS, int CH>
-__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc) {
+// Data movement: a warp-iteration covers one GROUP of 32 slots, whose records are one contiguous block (struct Rec).
+// The block of the NEXT iteration is fetched by a bulk copy into the other half of the warp's double buffer while the
+// current one is evaluated out of shared memory, so the FP64 pipe never waits on an L2 round trip; the first block of
+// the next sweep is fetched as this sweep ends (the records do not change during a solve) and is already waiting when
+// the controller publishes the next pose.
+template <int ALGO, int KC, int THREADS>
+__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc, GroupPipe& pp) {
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
-  const int nslots = a.sv.nslots;
-  const size_t ncorr = (size_t)nslots * KC;
-  // Work split: groups of 32 slots (one warp-iteration each).  A block owns a contiguous range of groups and deals
-  // them to its warps round-robin, so the four schedulers of an SM carry the same number of groups (+-1).
-  const int ngroups = nslots >> 5;
+  constexpr unsigned GB = Rec::group_bytes(KC);
+  constexpr int W = THREADS / 32;
+  // Work split: a block owns a contiguous range of groups and deals them to its warps round-robin, so the four
+  // schedulers of an SM carry the same number of groups (+-1).
+  const int ngroups = a.sv.nslots >> 5;
   const int g0 = (int)(((long long)ngroups * blockIdx.x) / gridDim.x), g1 = (int)(((long long)ngroups * (blockIdx.x + 1)) / gridDim.x);
   const int lane = threadIdx.x & 31;
-  for (int g = g0 + (threadIdx.x >> 5); g < g1; g += THREADS / 32) {
-    const int slot = (g << 5) + lane;
-    // every load of the slot is issued before the first use (one L2 round trip per warp-iteration)
-    double w[KC];
-    float4 tp[CH];
-    double u[CH][3];
-#pragma unroll
-    for (int c = 0; c < KC; c++) w[c] = __ldg(&a.w[(size_t)c * nslots + slot]);
-    if (CH == KC) {
-#pragma unroll
-      for (int c = 0; c < CH; c++) {
-        const size_t ro = (size_t)c * nslots + slot;
-        tp[c] = __ldg(&a.g_pt[ro]);
-        u[c][0] = __ldg(&a.g_nt[ro]); u[c][1] = __ldg(&a.g_nt[ncorr + ro]); u[c][2] = __ldg(&a.g_nt[2 * ncorr + ro]);
-      }
-    }
-    const float4 sp = __ldg(&a.sv.pts[slot]);
-    double ns[3] = {__ldg(&a.sv.nrm[slot]), __ldg(&a.sv.nrm[(size_t)nslots + slot]), __ldg(&a.sv.nrm[2 * (size_t)nslots + slot])};
-    bool any = false;
-#pragma unroll
-    for (int c = 0; c < KC; c++) any = any || (w[c] != 0.0);
-    // padding slots hold NaN coordinates and undefined normals; all their weights are 0, so zeroed geometry keeps the
-    // branch-free code below finite (0 * finite = 0) without a divergent skip
-    const double ps[3] = {any ? (double)sp.x : 0.0, any ? (double)sp.y : 0.0, any ? (double)sp.z : 0.0};
-#pragma unroll
-    for (int i = 0; i < 3; i++) ns[i] = any ? ns[i] : 0.0;
+  const int gfirst = g0 + (threadIdx.x >> 5);
+  if (gfirst >= g1) return;
+  const char* rec = a.rec;
+  if (!pp.primed && lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), rec + (size_t)gfirst * GB, GB, pp.bar + 8 * (pp.uses & 1));
+  for (int g = gfirst; g < g1; g += W) {
+    __syncwarp();  // every lane is done with the buffer the next copy lands in (it was read one iteration ago)
+    if (lane == 0 && g + W < g1) bulk_load(smem_u32(pp.buf + ((pp.uses + 1) & 1) * GB), rec + (size_t)(g + W) * GB, GB, pp.bar + 8 * ((pp.uses + 1) & 1));
+    mbar_wait(pp.bar + 8 * (pp.uses & 1), (pp.uses >> 1) & 1);
+    const char* blk = pp.buf + (pp.uses & 1) * GB;
+    pp.uses++;
+    const char* sb = blk + KC * Rec::kCandBytes;
+    const double ps[3] = {(double)reinterpret_cast<const float*>(sb + Rec::kSx)[lane], (double)reinterpret_cast<const float*>(sb + Rec::kSy)[lane],
+                          (double)reinterpret_cast<const float*>(sb + Rec::kSz)[lane]};
+    const double ns[3] = {reinterpret_cast<const double*>(sb + Rec::kSnx)[lane], reinterpret_cast<const double*>(sb + Rec::kSny)[lane],
+                          reinterpret_cast<const double*>(sb + Rec::kSnz)[lane]};
     double q0[3], qt[3], m[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {  // R, t are read from shared memory (broadcast) instead of pinning 24 registers
@@ -577,32 +611,28 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
       qt[i] = q0[i] + s_RT[9 + i];
       m[i] = r0 * ns[0] + r1 * ns[1] + r2 * ns[2];
     }
-#pragma unroll 1
-    for (int c0 = 0; c0 < KC; c0 += CH) {
-    if (CH != KC) {
 #pragma unroll
-      for (int c = 0; c < CH; c++) {
-        const size_t ro = (size_t)(c0 + c) * nslots + slot;
-        tp[c] = __ldg(&a.g_pt[ro]);
-        u[c][0] = __ldg(&a.g_nt[ro]); u[c][1] = __ldg(&a.g_nt[ncorr + ro]); u[c][2] = __ldg(&a.g_nt[2 * ncorr + ro]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < CH; c++) {
-      const double d[3] = {(double)tp[c].x - qt[0], (double)tp[c].y - qt[1], (double)tp[c].z - qt[2]};
+    for (int c = 0; c < KC; c++) {
+      const char* cb = blk + c * Rec::kCandBytes;
+      const double w = reinterpret_cast<const double*>(cb + Rec::kW)[lane];
+      const double u[3] = {reinterpret_cast<const double*>(cb + Rec::kNx)[lane], reinterpret_cast<const double*>(cb + Rec::kNy)[lane],
+                           reinterpret_cast<const double*>(cb + Rec::kNz)[lane]};
+      const double d[3] = {(double)reinterpret_cast<const float*>(cb + Rec::kPx)[lane] - qt[0],
+                           (double)reinterpret_cast<const float*>(cb + Rec::kPy)[lane] - qt[1],
+                           (double)reinterpret_cast<const float*>(cb + Rec::kPz)[lane] - qt[2]};
       // b = M d (rank-2 Woodbury, see apply_Minv)
-      const double cuv = u[c][0] * m[0] + u[c][1] * m[1] + u[c][2] * m[2];
-      const double pu = u[c][0] * d[0] + u[c][1] * d[1] + u[c][2] * d[2];
+      const double cuv = u[0] * m[0] + u[1] * m[1] + u[2] * m[2];
+      const double pu = u[0] * d[0] + u[1] * d[1] + u[2] * d[2];
       const double pm = m[0] * d[0] + m[1] * d[1] + m[2] * d[2];
       const double be = a.cfg.hk * cuv;
       const double idet = a.cfg.k4 * rcp_pos((a.cfg.aa - be) * (a.cfg.aa + be));
       const double g1c = (a.cfg.aa * pu + be * pm) * idet, g2c = (be * pu + a.cfg.aa * pm) * idet;
       double b[3];
 #pragma unroll
-      for (int i = 0; i < 3; i++) b[i] = 0.5 * d[i] + (g1c * u[c][i] + g2c * m[i]);
+      for (int i = 0; i < 3; i++) b[i] = 0.5 * d[i] + (g1c * u[i] + g2c * m[i]);
       const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
       double rho0, rho1;
-      loss_fast<ALGO>(CH == KC ? w[c] : pick_w<KC>(w, c0 + c), res, &rho0, &rho1);
+      loss_fast<ALGO>(w, res, &rho0, &rho1);
       const double mb = a.cfg.kappa * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]);
       const double v[3] = {q0[0] - mb * m[0], q0[1] - mb * m[1], q0[2] - mb * m[2]};
       double j[6], jw[6];
@@ -621,8 +651,16 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
       }
       acc[27] += rho0;
     }
-    }
   }
+  __syncwarp();
+  if (lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), rec + (size_t)gfirst * GB, GB, pp.bar + 8 * (pp.uses & 1));
+  pp.primed = true;
+}
+// a block may only exit (and hand its shared memory back) once no bulk copy is in flight into it
+template <int KC, int THREADS>
+__device__ __forceinline__ void pipe_drain(GroupPipe& pp) {
+  if (pp.primed) mbar_wait(pp.bar + 8 * (pp.uses & 1), (pp.uses >> 1) & 1);
+  pp.primed = false;
 }
 
 // Block reduction of the 28 per-thread sums through shared memory (fixed order => deterministic): every thread
@@ -709,9 +747,12 @@ __device__ __forceinline__ void rotate_totals(const double* s_tot, const double*
 // ONE 256-thread CTA per SM: with up to 255 registers per thread the k_c residual chains of a slot interleave without
 // spills, which feeds the FP64 pipe better than twice the warps at 128 registers (measured: 1.97 -> 1.76 ms of LM per
 // KITTI EM registration), and every CTA sees the same SM so none finishes early behind an older neighbour.
-template <int ALGO, int KC, int THREADS, int MINB, int CH>
+template <int ALGO, int KC, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
-  extern __shared__ double s_acc[];  // [kAcc][THREADS]
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  double* s_acc = reinterpret_cast<double*>(s_dyn);                          // [kAcc][THREADS] block_reduce staging
+  char* s_pipe = reinterpret_cast<char*>(s_dyn) + sizeof(double) * kAcc * THREADS;  // [THREADS/32][2][group bytes] record double buffers
+  __shared__ __align__(8) unsigned long long s_bar[2 * (THREADS / 32)];
   __shared__ LMState S;
   __shared__ double s_red[THREADS / 32][kAcc];
   __shared__ double s_tot[kAcc];
@@ -725,6 +766,16 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
   if (threadIdx.x < 7) s_x[threadIdx.x] = eval_only ? a.eval_pose[threadIdx.x] : a.ctl->pose[threadIdx.x];
   if (threadIdx.x == 7) s_x[7] = eval_only ? 0.0 : (double)a.ctl->converged;
   if (controller && threadIdx.x == 0) S.started = 0;
+  GroupPipe pp;
+  pp.buf = s_pipe + (size_t)(threadIdx.x >> 5) * 2 * Rec::group_bytes(KC);
+  pp.bar = smem_u32(&s_bar[2 * (threadIdx.x >> 5)]);
+  pp.uses = 0;
+  pp.primed = false;
+  if ((threadIdx.x & 31) == 0) {
+    mbar_init(pp.bar, 1);
+    mbar_init(pp.bar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   if (s_x[7] != 0.0) {  // registration already converged: passes enqueued ahead of the host return at once
     if (a.cond && controller && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0u);  // never leave a graph loop running
@@ -741,7 +792,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
     }
     __syncthreads();
     double acc[kAcc];
-    sweep_acc<ALGO, KC, THREADS, CH>(a, s_RT, acc);
+    sweep_acc<ALGO, KC, THREADS>(a, s_RT, acc, pp);
     block_reduce<THREADS>(acc, s_acc, a.partials);
     gen++;
     __syncthreads();  // the block's partial sums are written; thread 0's gpu-scope fence below is cumulative over them
@@ -752,7 +803,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
         __threadfence();
         atomicAdd(&sy->count, 1u);
       }
-      if (eval_only) return;
+      if (eval_only) { pipe_drain<KC, THREADS>(pp); return; }
       // lanes 0..7 spin on the generation flag (one transaction per poll; no nanosleep: its wake-up granularity is of the
       // order of a microsecond, longer than the whole control step it would be waiting for) and then fetch their word of
       // the broadcast record — flag and record share a 128-byte line
@@ -775,6 +826,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
       if (eval_only) {
         if (threadIdx.x < kAcc) a.eval_out[threadIdx.x] = s_rot[threadIdx.x];
         if (threadIdx.x == 0) sy->count = 0;
+        pipe_drain<KC, THREADS>(pp);
         return;
       }
       if (threadIdx.x < 32) {
@@ -826,6 +878,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
     }
     if (s_x[7] != 0.0) break;
   }
+  pipe_drain<KC, THREADS>(pp);
 #ifdef SICP_STATS
   if (threadIdx.x == 0 && blockIdx.x < 512) { atomicAdd(&g_lm_blk[blockIdx.x][0], (unsigned long long)t_comp); atomicAdd(&g_lm_blk[blockIdx.x][1], (unsigned long long)t_wait); }
 #endif
@@ -867,9 +920,8 @@ __global__ void fused_labels_kernel(CloudView sv, CloudView tv, double eps, doub
       apply_Minv(nt, m, d, kappa, b);
       const double mahal = -0.5 * (d[0] * b[0] + d[1] * b[1] + d[2] * b[2]);
       const double two_pi = 6.283185307179586;
-      const double density = pow((two_pi * two_pi * two_pi) * det_S(nt, m, kappa), -0.5) * exp(mahal);
       tsl[c] = ts;
-      gate[c] = (density == 0.0) ? 0.0 : 1.0;
+      gate[c] = (!(mahal > -700.0) && density_is_zero((two_pi * two_pi * two_pi) * det_S(nt, m, kappa), mahal)) ? 0.0 : 1.0;
     }
   }
   double best = 0.0; int best_s = 0;
@@ -889,15 +941,12 @@ __global__ void fused_labels_kernel(CloudView sv, CloudView tv, double eps, doub
 // leaves registers free lets the CTAs of OTHER registrations (a second solve in its control step, kNN kernels) use the
 // SM while this one waits — what a batch needs.
 struct LmShape { int threads, minb; };
-static const LmShape kLmShapes[kLmVariants] = {{256, 1}, {128, 1}, {256, 2}, {256, 2}, {512, 1}};
+static const LmShape kLmShapes[kLmVariants] = {{256, 1}, {128, 1}};
 template <int ALGO, int KC>
 static void* lm_entry_algo(int variant) {
   switch (variant) {
-    case 1: return (void*)lm_kernel<ALGO, KC, 128, 1, KC>;
-    case 2: return (void*)lm_kernel<ALGO, KC, 256, 2, 1>;
-    case 3: return (void*)lm_kernel<ALGO, KC, 256, 2, (KC >= 2 ? 2 : 1)>;
-    case 4: return (void*)lm_kernel<ALGO, KC, 512, 1, 1>;
-    default: return (void*)lm_kernel<ALGO, KC, 256, 1, KC>;
+    case 1: return (void*)lm_kernel<ALGO, KC, 128, 1>;
+    default: return (void*)lm_kernel<ALGO, KC, 256, 1>;
   }
 }
 static void* lm_entry(int algo, int variant) {
@@ -907,7 +956,11 @@ static void* lm_entry(int algo, int variant) {
     default: return lm_entry_algo<SICP_ALGO_EM, 4>(variant);
   }
 }
-static size_t lm_smem(int variant) { return sizeof(double) * kAcc * kLmShapes[variant].threads; }  // block_reduce staging (opt-in dynamic shared memory)
+// dynamic shared memory: block_reduce staging + the per-warp double buffers of record blocks
+static size_t lm_smem(int algo, int variant) {
+  const int t = kLmShapes[variant].threads, kc = algo == SICP_ALGO_EM ? 4 : 1;
+  return sizeof(double) * kAcc * t + (size_t)(t / 32) * 2 * Rec::group_bytes(kc);
+}
 // Largest cooperative grid of a shape on this device (co-resident CTAs), capped by the partials slab.
 int lm_max_grid(int device, int algo, int variant) {
   static int cached[64][3][kLmVariants] = {};
@@ -917,8 +970,8 @@ int lm_max_grid(int device, int algo, int variant) {
   int sms = 148, per_sm = 1;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   void* fn = lm_entry(algo, variant);
-  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem(variant));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLmShapes[variant].threads, lm_smem(variant)) != cudaSuccess || per_sm < 1) per_sm = 1;
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lm_smem(algo, variant));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kLmShapes[variant].threads, lm_smem(algo, variant)) != cudaSuccess || per_sm < 1) per_sm = 1;
   const int g = std::min(sms * per_sm, kLmMaxGrid);
   if (device >= 0 && device < 64) cached[device][ai][variant] = g;
   return g;
@@ -930,14 +983,13 @@ int lm_grid_blocks(int device) {  // lone-registration grid: one CTA of shape 0 
 }
 
 sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMConfig& cfg, double gate_d2, const double* d_pose7,
-                         const int* d_stop, int* d_corr, const float* d_d2, double* d_w, float4* d_gpt, double* d_gnt, RegCtl* d_ctl,
-                         cudaStream_t st) {
+                         const int* d_stop, int* d_corr, const float* d_d2, char* d_rec, RegCtl* d_ctl, cudaStream_t st) {
   if (src->nslots == 0) return SICP_OK;
   const unsigned grid = (unsigned)((src->nslots + kEstepThreads - 1) / kEstepThreads);
   if (cfg.kc == 4)
-    estep_kernel<4><<<grid, kEstepThreads, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w, d_gpt, d_gnt, d_ctl);
+    estep_kernel<4><<<grid, kEstepThreads, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_rec, d_ctl);
   else
-    estep_kernel<1><<<grid, kEstepThreads, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_w, d_gpt, d_gnt, d_ctl);
+    estep_kernel<1><<<grid, kEstepThreads, 0, st>>>(src->view(), tgt->view(), cfg.algo, cfg.eps, gate_d2, d_pose7, d_stop, d_corr, d_d2, d_rec, d_ctl);
   count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;
@@ -950,24 +1002,24 @@ static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
   grid = std::max(1, std::min(grid, lm_max_grid(dev, args.cfg.algo, variant)));  // also sets the shared-memory attribute
   args.partials = reinterpret_cast<double*>(args.sync) + kLmSyncDoubles;
   void* params[] = {&args};
-  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo, variant), dim3(grid), dim3(kLmShapes[variant].threads), params, lm_smem(variant), st));
+  SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo, variant), dim3(grid), dim3(kLmShapes[variant].threads), params, lm_smem(args.cfg.algo, variant), st));
   count_launches(1);
   return SICP_OK;
 }
 
 // d_partials: kLmSyncDoubles doubles of LMSync (zeroed once when the workspace is created; generations continue across
 // launches) followed by kLmMaxGrid * kAcc block partials.
-sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt, RegCtl* d_ctl,
+sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const char* d_rec, RegCtl* d_ctl,
                       double* d_partials, int grid, cudaStream_t st, unsigned long long cond_handle) {
-  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, d_ctl, nullptr, reinterpret_cast<LMSync*>(d_partials), nullptr, nullptr,
+  LMArgs args{src->view(), cfg, d_rec, d_ctl, nullptr, reinterpret_cast<LMSync*>(d_partials), nullptr, nullptr,
               (cudaGraphConditionalHandle)cond_handle};
   static_assert(sizeof(LMSync) <= sizeof(double) * kLmSyncDoubles, "LMSync must fit in front of the partials");
   return launch_lm_args(args, grid, st);
 }
 
-sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const double* d_w, const float4* d_gpt, const double* d_gnt,
+sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const char* d_rec,
                             const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st) {
-  LMArgs args{src->view(), cfg, d_w, d_gpt, d_gnt, nullptr, nullptr, reinterpret_cast<LMSync*>(d_partials), d_pose7, d_out28, 0};
+  LMArgs args{src->view(), cfg, d_rec, nullptr, nullptr, reinterpret_cast<LMSync*>(d_partials), d_pose7, d_out28, 0};
   return launch_lm_args(args, grid, st);
 }
 

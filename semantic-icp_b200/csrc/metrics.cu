@@ -94,8 +94,8 @@ sicp_status sicp_label_agreement(const sicp_cloud* src, const sicp_cloud* tgt, c
   SICP_CHECK(validate_pose7(pose7, "sicp_label_agreement", true));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(src->wait_built(st));
-  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(ensure_built(src, st));
+  SICP_CHECK(ensure_built(tgt, st));
   stats3_out[0] = stats3_out[1] = stats3_out[2] = 0.0;
   if (n_labels) std::memset(confusion_out, 0, sizeof(int64_t) * (size_t)n_labels * n_labels);
   if (src->nslots == 0) return SICP_OK;

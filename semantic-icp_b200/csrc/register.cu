@@ -102,8 +102,8 @@ static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, c
   }
   sicp_set_stream(saved);
   SICP_CHECK(rc);
-  SICP_CUDA(src->wait_ready(st));
-  SICP_CUDA(tgt->wait_ready(st));
+  SICP_CHECK(ensure_ready(src, st));
+  SICP_CHECK(ensure_ready(tgt, st));
   return SICP_OK;
 }
 
@@ -135,7 +135,8 @@ struct Slot {
   cudaStream_t st = nullptr;      // own stream (batch) — a lone registration runs on the caller's stream instead
   cudaStream_t cap = nullptr;     // capture-only stream for building the pass graph
   size_t cap_nc = 0;              // capacity in candidate records
-  int* d_corr = nullptr; float* d_d2 = nullptr; double* d_w = nullptr; float4* d_gpt = nullptr; double* d_gnt = nullptr;
+  int* d_corr = nullptr; float* d_d2 = nullptr;
+  char* d_rec = nullptr;         // record group blocks of the current pass (kernels.h: struct Rec), sized for k_c = 4
   RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
   RegCtl* h_ctl = nullptr;        // pinned
   int* h_map = nullptr;           // pinned, kMaxSegMap ints (class map staging)
@@ -164,16 +165,14 @@ struct Slot {
       const size_t want = nc + nc / 8;
       SICP_CUDA(cudaMalloc(&d_corr, sizeof(int) * want));
       SICP_CUDA(cudaMalloc(&d_d2, sizeof(float) * want));
-      SICP_CUDA(cudaMalloc(&d_w, sizeof(double) * want));
-      SICP_CUDA(cudaMalloc(&d_gpt, sizeof(float4) * want));
-      SICP_CUDA(cudaMalloc(&d_gnt, sizeof(double) * 3 * want));
+      SICP_CUDA(cudaMalloc(&d_rec, (want / 32 + 1) * (size_t)Rec::group_bytes(4)));  // want >= nslots * k_c: enough groups for either k_c
       cap_nc = want;
     }
     return SICP_OK;
   }
   void free_records() {
-    cudaFree(d_corr); cudaFree(d_d2); cudaFree(d_w); cudaFree(d_gpt); cudaFree(d_gnt);
-    d_corr = nullptr; d_d2 = nullptr; d_w = nullptr; d_gpt = nullptr; d_gnt = nullptr; cap_nc = 0;
+    cudaFree(d_corr); cudaFree(d_d2); cudaFree(d_rec);
+    d_corr = nullptr; d_d2 = nullptr; d_rec = nullptr; cap_nc = 0;
   }
   void destroy() {
     if (device < 0) return;
@@ -264,10 +263,10 @@ struct Job {
     SICP_CHECK(launch_cross_knn(src, tgt, sl->d_ctl->pose, stop, class_map(), cfg.kc, sl->d_corr, sl->d_d2, s));
     tm.end(s);
     tm.begin(SICP_STAGE_ESTEP, s);
-    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, sl->d_ctl->pose, stop, sl->d_corr, sl->d_d2, sl->d_w, sl->d_gpt, sl->d_gnt, sl->d_ctl, s));
+    SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, sl->d_ctl->pose, stop, sl->d_corr, sl->d_d2, sl->d_rec, sl->d_ctl, s));
     tm.end(s);
     tm.begin(SICP_STAGE_LM, s);
-    SICP_CHECK(launch_lm(src, cfg, sl->d_w, sl->d_gpt, sl->d_gnt, sl->d_ctl, sl->d_partials, lm_grid, s, cond));
+    SICP_CHECK(launch_lm(src, cfg, sl->d_rec, sl->d_ctl, sl->d_partials, lm_grid, s, cond));
     tm.end(s);
     return SICP_OK;
   }
@@ -393,8 +392,8 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     jb.tm.on = jb.opts->profile != 0;
     jb.trace_ref = fork; jb.trace_id = j;
     // the clouds may still be building on the stream (or host thread) that created them
-    SICP_CUDA(jb.src->wait_built(jb.st));
-    SICP_CUDA(jb.tgt->wait_built(jb.st));
+    SICP_CHECK(ensure_built(jb.src, jb.st));
+    SICP_CHECK(ensure_built(jb.tgt, jb.st));
     jb.tm.begin(SICP_STAGE_COV, jb.st);
     const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, jb.st, lone ? t_helper : nullptr);
     jb.tm.end(jb.st);
@@ -404,9 +403,17 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     live++;
     return SICP_OK;
   };
+  // SICP_HOSTSTAT=1: where the host thread's time goes (issuing work vs asleep waiting for a slot) — tuning aid
+  const bool hoststat = env_int("SICP_HOSTSTAT", 0) != 0;
+  auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_issue = 0, t_wait = 0, t_begin = now_ms(), t0 = t_begin;
   for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch(s);
+  t_issue += now_ms() - t0;
   while (live > 0 && rc == SICP_OK) {
+    t0 = now_ms();
     const int s = done_q.pop();  // sleeps until some slot's readback has landed
+    t_wait += now_ms() - t0;
+    t0 = now_ms();
     const int j = slot_job[s];
     if (j < 0) continue;
     if (jobs[j].complete()) {
@@ -417,7 +424,10 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     } else {
       rc = jobs[j].advance(kChunk);
     }
+    t_issue += now_ms() - t0;
   }
+  if (hoststat)
+    fprintf(stderr, "[sicp] run_jobs: %d jobs, %d slots, %.2f ms wall: host issuing %.2f ms, asleep %.2f ms\n", nj, S, now_ms() - t_begin, t_issue, t_wait);
   if (rc != SICP_OK) cudaDeviceSynchronize();  // error path: nothing may still be writing a pinned control block
   for (int s = 0; s < S; s++) t_pool.get(s)->note.c = nullptr;
   if (!lone) {
@@ -495,8 +505,8 @@ sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, con
   SICP_CHECK(validate_pose7(pose7, "sicp_correspondences"));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(src->wait_built(st));
-  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(ensure_built(src, st));
+  SICP_CHECK(ensure_built(tgt, st));
   SICP_CHECK(precompute_pair(algo, src, tgt, opts, st, nullptr));
   Job jb;
   jb.algo = algo; jb.src = src; jb.tgt = tgt; jb.opts = opts; jb.cfg = make_cfg(algo, *opts); jb.st = st;
@@ -504,14 +514,15 @@ sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, con
   Slot* ws = jb.sl;
   LMConfig& cfg = jb.cfg;
   const size_t nslot_c = (size_t)src->nslots * cfg.kc;
-  std::vector<int> h_corr(nslot_c); std::vector<float> h_d2(nslot_c); std::vector<double> h_w(nslot_c);
+  const size_t rec_bytes = (size_t)(src->nslots / 32) * Rec::group_bytes(cfg.kc);
+  std::vector<int> h_corr(nslot_c); std::vector<float> h_d2(nslot_c); std::vector<char> h_rec(rec_bytes);
   std::vector<float4> h_spts(src->nslots), h_tpts(tgt->nslots);
   SICP_CHECK(jb.start(pose7));
   SICP_CHECK(launch_cross_knn(src, tgt, ws->d_ctl->pose, nullptr, jb.class_map(), cfg.kc, ws->d_corr, ws->d_d2, st));
-  SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws->d_ctl->pose, nullptr, ws->d_corr, ws->d_d2, ws->d_w, ws->d_gpt, ws->d_gnt, nullptr, st));
+  SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws->d_ctl->pose, nullptr, ws->d_corr, ws->d_d2, ws->d_rec, nullptr, st));
   SICP_CUDA(cudaMemcpyAsync(h_corr.data(), ws->d_corr, sizeof(int) * nslot_c, cudaMemcpyDeviceToHost, st));
   SICP_CUDA(cudaMemcpyAsync(h_d2.data(), ws->d_d2, sizeof(float) * nslot_c, cudaMemcpyDeviceToHost, st));
-  SICP_CUDA(cudaMemcpyAsync(h_w.data(), ws->d_w, sizeof(double) * nslot_c, cudaMemcpyDeviceToHost, st));
+  SICP_CUDA(cudaMemcpyAsync(h_rec.data(), ws->d_rec, rec_bytes, cudaMemcpyDeviceToHost, st));
   SICP_CUDA(cudaMemcpyAsync(h_spts.data(), src->d_pts, sizeof(float4) * src->nslots, cudaMemcpyDeviceToHost, st));
   SICP_CUDA(cudaMemcpyAsync(h_tpts.data(), tgt->d_pts, sizeof(float4) * tgt->nslots, cudaMemcpyDeviceToHost, st));
   SICP_CUDA(cudaStreamSynchronize(st));
@@ -523,7 +534,11 @@ sicp_status sicp_correspondences(int algo, sicp_cloud* src, sicp_cloud* tgt, con
       int to = -1;
       if (ts >= 0) std::memcpy(&to, &h_tpts[ts].w, 4);
       idx_out[(size_t)o * cfg.kc + c] = to;
-      if (w_out) w_out[(size_t)o * cfg.kc + c] = h_w[(size_t)c * src->nslots + s];  // gathered arrays are c-major
+      if (w_out) {  // weight of record (slot s, candidate c): group block s / 32, lane s % 32
+        double wv;
+        std::memcpy(&wv, h_rec.data() + (size_t)(s >> 5) * Rec::group_bytes(cfg.kc) + c * Rec::kCandBytes + Rec::kW + 8 * (s & 31), 8);
+        w_out[(size_t)o * cfg.kc + c] = wv;
+      }
       if (d2_out) d2_out[(size_t)o * cfg.kc + c] = h_d2[(size_t)s * cfg.kc + c];
     }
   }
@@ -538,8 +553,8 @@ sicp_status sicp_evaluate(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp
   SICP_CHECK(validate_pose7(eval_pose7, "sicp_evaluate (eval_pose7)"));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(src->wait_built(st));
-  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(ensure_built(src, st));
+  SICP_CHECK(ensure_built(tgt, st));
   SICP_CHECK(precompute_pair(algo, src, tgt, opts, st, nullptr));
   Job jb;
   jb.algo = algo; jb.src = src; jb.tgt = tgt; jb.opts = opts; jb.cfg = make_cfg(algo, *opts); jb.st = st;
@@ -552,9 +567,9 @@ sicp_status sicp_evaluate(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp
   std::memcpy(ws->h_ctl->pass_pose[0], eval_pose7, 56);  // scratch row for the evaluation pose
   SICP_CUDA(cudaMemcpyAsync(ws->d_ctl, ws->h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
   SICP_CHECK(launch_cross_knn(src, tgt, ws->d_ctl->pose, nullptr, jb.class_map(), cfg.kc, ws->d_corr, ws->d_d2, st));
-  SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws->d_ctl->pose, nullptr, ws->d_corr, ws->d_d2, ws->d_w, ws->d_gpt, ws->d_gnt, nullptr, st));
+  SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, ws->d_ctl->pose, nullptr, ws->d_corr, ws->d_d2, ws->d_rec, nullptr, st));
   double* d_out = &ws->d_ctl->pass_pose[8][0];
-  SICP_CHECK(launch_evaluate(src, cfg, ws->d_w, ws->d_gpt, ws->d_gnt, &ws->d_ctl->pass_pose[0][0], d_out, ws->d_partials, lm_grid_blocks(src->device), st));
+  SICP_CHECK(launch_evaluate(src, cfg, ws->d_rec, &ws->d_ctl->pass_pose[0][0], d_out, ws->d_partials, lm_grid_blocks(src->device), st));
   double* h_out = &ws->h_ctl->pass_pose[8][0];  // pinned
   SICP_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * 28, cudaMemcpyDeviceToHost, st));
   SICP_CUDA(cudaStreamSynchronize(st));
@@ -572,8 +587,8 @@ sicp_status sicp_fused_labels(sicp_cloud* src, sicp_cloud* tgt, const sicp_optio
   SICP_CHECK(validate_pose7(pose7, "sicp_fused_labels"));
   SICP_CUDA(cudaSetDevice(src->device));
   cudaStream_t st = current_stream();
-  SICP_CUDA(src->wait_built(st));
-  SICP_CUDA(tgt->wait_built(st));
+  SICP_CHECK(ensure_built(src, st));
+  SICP_CHECK(ensure_built(tgt, st));
   SICP_CHECK(precompute_pair(SICP_ALGO_EM, src, tgt, opts, st, nullptr));
   Job jb;
   jb.algo = SICP_ALGO_EM; jb.src = src; jb.tgt = tgt; jb.opts = opts; jb.cfg = make_cfg(SICP_ALGO_EM, *opts); jb.st = st;

@@ -286,6 +286,55 @@ def kitti_sequence(n_frames, n_points=120_000, N=20, seed=4000, n_rings=64, n_az
     return frames, poses, cm
 
 
+# ----------------------------------------------------------------------------- C4: long odometry sequence
+# kitti_sequence() above keeps ONE 100 m scene, which a 1,000-frame drive leaves after ~80 frames (the rest would be
+# ground + parallel facades only: degenerate for any ICP).  The long sequence tiles independently seeded scenes every
+# 100 m along +x; a frame sees the tiles within sensor range.  Frames are generated independently (parallel, cacheable).
+_TILE = 100.0
+
+
+def _tile_scene(tile, N, seed):
+    sc = kitti_scene(np.random.default_rng(seed + 7919 * (tile + 1000)), N)
+    dx = np.array([_TILE * tile, 0.0, 0.0])
+    out = Scene()
+    out.boxes = [(lo + dx, hi + dx, c) for (lo, hi, c) in sc.boxes]
+    out.cyls = [(cx + dx[0], cy, r, z0, z1, c) for (cx, cy, r, z0, z1, c) in sc.cyls]
+    return out, sc.planes
+
+
+def kitti_long_poses(n_frames):
+    """Sensor poses (R, t) of the long sequence: 1 m per frame along a lane that weaves +-1.5 m (heading within +-1.5 deg),
+    so the drive stays between the facades for any length."""
+    poses = []
+    for f in range(n_frames):
+        x = 1.0 * f
+        y = 1.5 * np.sin(x / 60.0)
+        psi = np.arctan(1.5 / 60.0 * np.cos(x / 60.0))
+        poses.append((_yaw(psi), np.array([x, y, 1.73])))
+    return poses
+
+
+def kitti_long_frame(f, n_frames=1001, n_points=120_000, N=20, seed=4000, n_rings=64, n_az=1875):
+    """Frame f of the C4 sequence: dict(xyz, labels, R, t, cm)."""
+    R, t = kitti_long_poses(n_frames)[f]
+    k0 = int(np.floor(t[0] / _TILE))
+    sc = Scene()
+    planes = None
+    for tile in (k0 - 1, k0, k0 + 1):
+        ts, pl = _tile_scene(tile, N, seed)
+        sc.boxes += ts.boxes
+        sc.cyls += ts.cyls
+        if tile == k0:
+            planes = pl
+    # ground + the two facades of the current tile, the facades shifted to the sensor's x (they span +-200 m)
+    sc.planes = [planes[0]] + [(p0 + np.array([_TILE * k0, 0, 0]), n, (b[0] + np.array([_TILE * k0, 0, 0]), b[1] + np.array([_TILE * k0, 0, 0])), c)
+                               for (p0, n, b, c) in planes[1:]]
+    frng = np.random.default_rng(seed + 1 + f)
+    cm = confusion_matrix(N, 0.8)
+    xyz, cls = lidar_scan(frng, sc, R, t, n_points, n_rings=n_rings, n_az=n_az)
+    return dict(xyz=xyz, labels=observe_labels(frng, cls, cm), R=R, t=t, cm=cm)
+
+
 def relative_pose(pose_t, pose_s):
     (Rt, tt), (Rs, ts) = pose_t, pose_s
     return pose7(Rt.T @ Rs, Rt.T @ (ts - tt))

@@ -120,6 +120,25 @@ def test_covariance_neighbours_normals_label_vectors(sicp, oracle, kitti_small):
     assert np.max(np.abs(c.label_vectors() - a_ref)) <= 1e-14
 
 
+def test_self_neighbours_with_exact_ties(sicp, oracle):
+    # integer lattice + duplicated points: whole shells of exactly equal distances straddle the 20th neighbour, so the
+    # covariance search has to break ties by original index
+    g = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(5), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([g, g[rng.integers(0, len(g), 150)]])
+    rng.shuffle(pts)
+    for k in (20, 12):
+        c = sicp.Cloud(pts)
+        c.precompute(k, 1e-3)
+        ridx, _ = oracle.knn(pts, pts, k, brute=True)
+        assert np.array_equal(c.self_neighbours(), ridx)
+    flat = np.concatenate([g[:, :2], np.zeros((len(g), 1), np.float32)], 1)  # every point 5 times: ties of 5, 20, 45 ... candidates
+    c = sicp.Cloud(flat)
+    c.precompute(20, 1e-3)
+    ridx, _ = oracle.knn(flat, flat, 20, brute=True)
+    assert np.array_equal(c.self_neighbours(), ridx)
+
+
 def test_covariance_per_class(sicp, oracle, room):
     p = room
     c = sicp.Cloud(p["src_xyz"], p["src_labels"], layout=sicp.CLOUD_PER_CLASS)
@@ -168,13 +187,17 @@ def test_first_pass_correspondences_and_weights(sicp, oracle, room, algo):
     assert np.max(np.abs(w - ref["w0"])) <= 1e-12 * max(1.0, np.max(np.abs(ref["w0"])))
 
 
-@pytest.mark.parametrize("algo,loss", [("gicp", 0), ("em", 2)])
+@pytest.mark.parametrize("algo,loss", [("gicp", 0), ("em", 2), ("semantic", 1)])
 def test_evaluate_cost_gradient_hessian(sicp, oracle, room, algo, loss):
     p = room
     a, src, tgt, opts = _algo_setup(sicp, p, algo)
     idx, w, _ = sicp.correspondences(a, src, tgt, opts, p["init"])
-    scov = oracle.covariances(p["src_xyz"], 20, 1e-3)["cov"]
-    tcov = oracle.covariances(p["tgt_xyz"], 20, 1e-3)["cov"]
+    if algo == "semantic":  # SemanticPointCloud covariances: neighbours restricted to the point's class (semantic_point_cloud.hpp:25-84)
+        scov = oracle.covariances_per_class(p["src_xyz"], p["src_labels"], 20, 1e-3)["cov"]
+        tcov = oracle.covariances_per_class(p["tgt_xyz"], p["tgt_labels"], 20, 1e-3)["cov"]
+    else:
+        scov = oracle.covariances(p["src_xyz"], 20, 1e-3)["cov"]
+        tcov = oracle.covariances(p["tgt_xyz"], 20, 1e-3)["cov"]
     kc = idx.shape[1]
     s_idx = np.repeat(np.arange(src.n), kc)[idx.ravel() >= 0]
     t_idx = idx.ravel()[idx.ravel() >= 0]
@@ -236,8 +259,43 @@ def test_fused_labels(sicp, oracle, room):
     a, src, tgt, opts = _algo_setup(sicp, p, "em")
     got = sicp.fused_labels(src, tgt, opts, p["T_gt"])
     ref = oracle.fused_labels(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], p["T_gt"])
-    # arg-max over f64 sums whose summation order differs by <=1e-15: allow a handful of exact-tie flips
     assert np.mean(got == ref) > 0.9995
+    # every mismatch must be an exact tie of the arg-max (f64 sums whose order differs by <= 1e-15): recompute the class
+    # scores of the mismatching points from the GPU's own label vectors and 4-NN lists
+    mism = np.nonzero(got != ref)[0]
+    if len(mism):
+        idx, d2 = sicp.knn(tgt, p["src_xyz"], 4, pose7=p["T_gt"])
+        a_s, a_t = src.label_vectors(), tgt.label_vectors()
+        unchecked = 0
+        for i in mism:
+            keep = (idx[i] >= 0) & (d2[i] < 250)
+            if np.any(d2[i][keep] >= 1.0):  # a far candidate could be gated by the bool-Probability rule: not recomputed here
+                unchecked += 1
+                continue
+            sc = (a_t[idx[i][keep]] * a_s[i]).sum(0)
+            top = np.sort(sc)
+            assert top[-1] - top[-2] <= 1e-12 * max(top[-1], 1e-300), (i, top[-2:])
+            assert sc[got[i] - 1] >= top[-1] * (1 - 1e-12)
+        assert unchecked <= 2
+
+
+def test_probability_gate_zeroes_weights(sicp, oracle, room):
+    """GICPCostFunction::Probability -> bool (gicp_cost_function.h:75-87, em_icp.hpp:108): with the tiny epsilon of
+    exec/scenenet_eval.cc:174 the Gaussian density underflows to exactly 0 for candidates far off the target plane (here
+    an initial pose 0.9 m too high), and those weights must come out as exact zeros — the same ones as the oracle's."""
+    p = room
+    eps = 1e-6
+    init = np.array([0, 0, 0, 1.0, 0, 0, 0.9])
+    src, tgt = sicp.Cloud(p["src_xyz"], p["src_labels"]), sicp.Cloud(p["tgt_xyz"], p["tgt_labels"])
+    opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"], epsilon=eps)
+    idx, w, d2 = sicp.correspondences(sicp.ALGO_EM, src, tgt, opts, init)
+    ref = oracle.align_em(p["src_xyz"], p["src_labels"], p["tgt_xyz"], p["tgt_labels"], p["cm"], init, eps=eps)
+    assert np.array_equal(idx, ref["corr0"])
+    zero_gpu, zero_ref = (idx >= 0) & (w == 0.0), (ref["corr0"] >= 0) & (ref["w0"] == 0.0)
+    assert zero_gpu.sum() > 1000                     # the underflow branch is really taken (label-compat alone is > 0 here)
+    assert (idx >= 0).sum() - zero_gpu.sum() > 100   # ... and not for everything
+    assert np.array_equal(zero_gpu, zero_ref)
+    assert np.max(np.abs(w - ref["w0"])) <= 1e-12 * max(1.0, np.max(np.abs(ref["w0"])))
 
 
 def test_errors(sicp, room):
@@ -255,6 +313,20 @@ def test_errors(sicp, room):
         sicp.register(sicp.ALGO_GICP, g, g, sicp.default_options(sicp.ALGO_GICP), np.array([0, 0, 0, 2.0, 0, 0, 0]))
     with pytest.raises(sicp.SicpError, match="unit quaternion"):
         sicp.register(sicp.ALGO_GICP, g, g, sicp.default_options(sicp.ALGO_GICP), np.array([0, 0, 0, 1.0, np.nan, 0, 0]))
+    # every C-ABI entry point that takes a pose validates it (finite, unit quaternion)
+    bad = np.array([0, 0, 0, 2.0, 0, 0, 0])
+    lab = sicp.Cloud(room["src_xyz"], room["src_labels"])
+    eopts = sicp.default_options(sicp.ALGO_EM, cm=room["cm"])
+    gopts = sicp.default_options(sicp.ALGO_GICP)
+    for call in (lambda: sicp.correspondences(sicp.ALGO_GICP, g, g, gopts, bad),
+                 lambda: sicp.evaluate(sicp.ALGO_GICP, g, g, gopts, room["init"], bad),
+                 lambda: sicp.evaluate(sicp.ALGO_GICP, g, g, gopts, bad, room["init"]),
+                 lambda: sicp.fused_labels(lab, lab, eopts, bad),
+                 lambda: sicp.knn(g, room["src_xyz"][:10], 1, pose7=bad),
+                 lambda: sicp.label_agreement(lab, lab, 11, pose7=bad),
+                 lambda: g.transform_f32(bad)):
+        with pytest.raises(sicp.SicpError, match="unit quaternion"):
+            call()
 
 
 # ------------------------------------------------------------------------------------------------ degenerate inputs
