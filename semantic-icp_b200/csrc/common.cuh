@@ -78,7 +78,7 @@ struct CloudView {
   const float4* node_hi;
   const uint32_t* leaf_key; // [nleaf_total] 30-bit Morton code of each leaf's first point (ascending inside a segment)
   const int* bb;            // [8] ordered-int bounding box of the cloud (the Morton quantisation frame)
-  const double* nrm;     // [3*nslots] SoA normals nx | ny | nz  (after precompute)
+  const double* nrm;     // [nslots][4] normals (nx, ny, nz, 0): one 32-byte sector per gathered normal  (after precompute)
   const double* avec;    // [nslots*N] label vectors a_p = CM^T dist_p (EM)
   int N;
 };

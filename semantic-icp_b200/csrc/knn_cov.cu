@@ -175,9 +175,7 @@ __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, co
   }
   double nv[3];
   mo.normal(k, nv);
-  nrm[slot] = nv[0];
-  nrm[(size_t)cv.nslots + slot] = nv[1];
-  nrm[2 * (size_t)cv.nslots + slot] = nv[2];
+  reinterpret_cast<double4*>(nrm)[slot] = make_double4(nv[0], nv[1], nv[2], 0.0);
 }
 
 // ------------------------------------------------------------------ K1b: label distribution -> a_p = CM^T dist_p
@@ -290,7 +288,8 @@ __global__ void unsort_rows_kernel(CloudView cv, const double* __restrict__ in, 
   if (slot >= cv.nslots) return;
   const int o = __float_as_int(cv.pts[slot].w);
   if (o < 0) return;
-  for (int c = 0; c < cols; c++) out[(size_t)o * cols + c] = soa ? in[(size_t)c * cv.nslots + slot] : in[(size_t)slot * cols + c];
+  // soa: 0 = rows of `cols`, 1 = SoA planes, 2 = rows padded to 4 doubles (normals)
+  for (int c = 0; c < cols; c++) out[(size_t)o * cols + c] = soa == 1 ? in[(size_t)c * cv.nslots + slot] : soa == 2 ? in[4 * (size_t)slot + c] : in[(size_t)slot * cols + c];
 }
 // normals (SoA, slot order) -> covariances I - (1-eps) n n^T in original order
 __global__ void cov_rows_kernel(CloudView cv, double eps, double* __restrict__ out) {
@@ -298,7 +297,7 @@ __global__ void cov_rows_kernel(CloudView cv, double eps, double* __restrict__ o
   if (slot >= cv.nslots) return;
   const int o = __float_as_int(cv.pts[slot].w);
   if (o < 0) return;
-  const double n[3] = {cv.nrm[slot], cv.nrm[(size_t)cv.nslots + slot], cv.nrm[2 * (size_t)cv.nslots + slot]};
+  const double n[3] = {cv.nrm[4 * (size_t)slot], cv.nrm[4 * (size_t)slot + 1], cv.nrm[4 * (size_t)slot + 2]};
   const double kap = 1.0 - eps;
   for (int a = 0; a < 3; a++)
     for (int b = 0; b < 3; b++) out[(size_t)o * 9 + 3 * a + b] = (a == b ? 1.0 : 0.0) - kap * n[a] * n[b];
@@ -405,7 +404,7 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
     SICP_CUDA(cudaDeviceSynchronize());
   }
   c->pre_valid = false;
-  if (!c->d_nrm) SICP_CUDA(cudaMallocAsync(&c->d_nrm, sizeof(double) * 3 * std::max(1, c->nslots), st));
+  if (!c->d_nrm) SICP_CUDA(cudaMallocAsync(&c->d_nrm, sizeof(double) * 4 * std::max(1, c->nslots), st));
   if (c->d_avec) { SICP_CUDA(cudaFreeAsync(c->d_avec, st)); c->d_avec = nullptr; }
   uint8_t* d_nbr = nullptr;
   double* d_cm = nullptr;
@@ -463,7 +462,7 @@ sicp_status sicp_cloud_get_normals(const sicp_cloud* c, double* out) {
   SICP_REQUIRE(c && out, "null argument");
   if (!c->pre_valid) { set_error("precompute has not run"); return SICP_ERR_STATE; }
   SICP_CUDA(cudaSetDevice(c->device));
-  return download_rows(c, c->d_nrm, 3, 1, out);
+  return download_rows(c, c->d_nrm, 3, 2, out);
 }
 sicp_status sicp_cloud_get_covariances(const sicp_cloud* c, double* out) {
   SICP_REQUIRE(c && out, "null argument");
@@ -498,7 +497,7 @@ sicp_status sicp_cloud_get_label_distributions(const sicp_cloud* c, double* out)
   SICP_CUDA(cudaMallocAsync(&d_cm, sizeof(double) * N * N, st));
   SICP_CUDA(cudaMallocAsync(&d_dist, sizeof(double) * N * std::max(1, c->nslots), st));
   SICP_CUDA(cudaMallocAsync(&d_a, sizeof(double) * N * std::max(1, c->nslots), st));
-  SICP_CUDA(cudaMallocAsync(&d_n, sizeof(double) * 3 * std::max(1, c->nslots), st));
+  SICP_CUDA(cudaMallocAsync(&d_n, sizeof(double) * 4 * std::max(1, c->nslots), st));
   SICP_CUDA(cudaMemcpyAsync(d_cm, c->pre_cm.data(), sizeof(double) * N * N, cudaMemcpyHostToDevice, st));
   SICP_CUDA(cudaMemsetAsync(d_dist, 0, sizeof(double) * N * std::max(1, c->nslots), st));
   SICP_CHECK(launch_self_knn_pca(c, c->pre_k, d_n, nullptr, d_nbr, st));
@@ -517,7 +516,7 @@ sicp_status sicp_cloud_get_self_neighbours(const sicp_cloud* c, int32_t* out) {
   int* d_nn; int32_t* d_out; double* d_n;
   SICP_CUDA(cudaMallocAsync(&d_nn, sizeof(int) * k * std::max(1, c->nslots), st));
   SICP_CUDA(cudaMallocAsync(&d_out, sizeof(int32_t) * k * std::max<size_t>(1, c->n), st));
-  SICP_CUDA(cudaMallocAsync(&d_n, sizeof(double) * 3 * std::max(1, c->nslots), st));
+  SICP_CUDA(cudaMallocAsync(&d_n, sizeof(double) * 4 * std::max(1, c->nslots), st));
   SICP_CHECK(launch_self_knn_pca(c, k, d_n, d_nn, nullptr, st));
   if (c->nslots) unsort_selfnn_kernel<<<(c->nslots + 255) / 256, 256, 0, st>>>(c->view(), k, d_nn, d_out);
   SICP_CUDA(cudaMemcpyAsync(out, d_out, sizeof(int32_t) * k * c->n, cudaMemcpyDeviceToHost, st));

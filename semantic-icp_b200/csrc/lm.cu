@@ -30,9 +30,9 @@ struct RT { double R[9]; double t[3]; };
 __device__ __forceinline__ void load_point(const CloudView& v, int slot, double* p, double* n) {
   const float4 a = __ldg(&v.pts[slot]);
   p[0] = a.x; p[1] = a.y; p[2] = a.z;
-  n[0] = __ldg(&v.nrm[slot]);
-  n[1] = __ldg(&v.nrm[(size_t)v.nslots + slot]);
-  n[2] = __ldg(&v.nrm[2 * (size_t)v.nslots + slot]);
+  const double2 a01 = __ldg(reinterpret_cast<const double2*>(v.nrm) + 2 * (size_t)slot);
+  n[0] = a01.x; n[1] = a01.y;
+  n[2] = __ldg(&v.nrm[4 * (size_t)slot + 2]);
 }
 
 // b = M d with M = (2I - kappa(u u^T + v v^T))^-1
@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, Clou
   for (int c = 0; c < KC; c++) {
     const int t = ts[c] >= 0 ? ts[c] : 0;
     tp[c] = __ldg(&tv.pts[t]);
-    nt[c][0] = __ldg(&tv.nrm[t]); nt[c][1] = __ldg(&tv.nrm[(size_t)tv.nslots + t]); nt[c][2] = __ldg(&tv.nrm[2 * (size_t)tv.nslots + t]);
+    const double2 n01 = __ldg(reinterpret_cast<const double2*>(tv.nrm) + 2 * (size_t)t);
+    nt[c][0] = n01.x; nt[c][1] = n01.y; nt[c][2] = __ldg(&tv.nrm[4 * (size_t)t + 2]);
     if (ts[c] >= 0) w[c] = 1.0;
   }
   double ps[3], ns[3];

@@ -7,6 +7,7 @@
 #define SICP_FACADE_PCL_IO_MIN_H_
 #include <cstdint>
 #include <cstring>
+#include <exception>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -61,16 +62,34 @@ int loadPCDFile(const std::string& file_name, pcl::PointCloud<PointT>& cloud) {
   }
   if (fields.empty() || data_mode.empty()) return -1;
   if (points == 0) points = width * height;
-  int ix = -1, iy = -1, iz = -1, il = -1, stride = 0;
+  // The header is untrusted input: only the SIZE / TYPE / COUNT combinations of the format are accepted, and the point
+  // count must fit the bytes that are actually left in the file (a record is at least one byte, in ascii two per value).
+  const std::streampos data_pos = in.tellg();
+  in.seekg(0, std::ios::end);
+  const std::streamoff remaining = in.tellg() - data_pos;
+  in.seekg(data_pos);
+  if (remaining < 0) return -1;
+  int ix = -1, iy = -1, iz = -1, il = -1;
+  long long stride = 0;
   for (std::size_t i = 0; i < fields.size(); i++) {
-    fields[i].offset = stride;
-    stride += fields[i].size * fields[i].count;
+    const detail::Field& f = fields[i];
+    const bool size_ok = f.type == 'F' ? (f.size == 4 || f.size == 8) : ((f.type == 'U' || f.type == 'I') && (f.size == 1 || f.size == 2 || f.size == 4 || f.size == 8));
+    if (!size_ok || f.count < 1 || f.count > (1 << 20)) return -1;
+    fields[i].offset = (int)stride;
+    stride += (long long)f.size * f.count;
+    if (stride > (1 << 24)) return -1;
     if (fields[i].name == "x") ix = (int)i; else if (fields[i].name == "y") iy = (int)i; else if (fields[i].name == "z") iz = (int)i;
     else if (fields[i].name == "label") il = (int)i;
   }
-  if (ix < 0 || iy < 0 || iz < 0) return -1;
+  if (ix < 0 || iy < 0 || iz < 0 || stride <= 0) return -1;
+  if (data_mode == "binary" ? (unsigned long long)points > (unsigned long long)remaining / (unsigned long long)stride
+                            : (unsigned long long)points > (unsigned long long)remaining) return -1;
   cloud.points.clear();
-  cloud.points.reserve(points);
+  try {
+    cloud.points.reserve(points);
+  } catch (const std::exception&) {
+    return -1;
+  }
   if (data_mode == "ascii") {
     for (std::size_t n = 0; n < points; n++) {
       PointT p;
@@ -85,7 +104,12 @@ int loadPCDFile(const std::string& file_name, pcl::PointCloud<PointT>& cloud) {
       cloud.points.push_back(p);
     }
   } else if (data_mode == "binary") {
-    std::vector<char> buf((std::size_t)stride * points);
+    std::vector<char> buf;
+    try {
+      buf.resize((std::size_t)stride * points);
+    } catch (const std::exception&) {
+      return -1;
+    }
     in.read(buf.data(), (std::streamsize)buf.size());
     if ((std::size_t)in.gcount() != buf.size()) return -1;
     for (std::size_t n = 0; n < points; n++) {

@@ -22,10 +22,15 @@ class DeviceKdTree {
     cloud_ = cloud;
     handle_ = detail::upload_whole(*cloud);
   }
+  // Same, but the device upload / build is postponed to the first search (SemanticPointCloud::addSemanticClouds)
+  void setInputCloudLazy(const PointCloudPtr& cloud) {
+    cloud_ = cloud;
+    handle_.reset();
+  }
   PointCloudPtr getInputCloud() const { return cloud_; }
   // pcl::KdTreeFLANN::nearestKSearch: returns the number of neighbours found (k clamped to the cloud size)
   int nearestKSearch(const PointT& p, int k, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances) const {
-    if (!handle_) throw std::runtime_error("semanticicp (B200): DeviceKdTree::nearestKSearch before setInputCloud");
+    ensure();
     const float q[3] = {p.x, p.y, p.z};
     std::vector<std::int32_t> idx(k);
     std::vector<float> d2(k);
@@ -38,7 +43,7 @@ class DeviceKdTree {
   }
   // Batched form (one launch for all queries): idx / d2 are nq x k, row-major, -1 / +inf where fewer than k exist.
   void nearestKSearchBatch(const pcl::PointCloud<PointT>& queries, int k, std::vector<int>& idx, std::vector<float>& d2) const {
-    if (!handle_) throw std::runtime_error("semanticicp (B200): DeviceKdTree::nearestKSearchBatch before setInputCloud");
+    ensure();
     const std::size_t nq = queries.points.size();
     std::vector<float> q(3 * nq);
     for (std::size_t i = 0; i < nq; i++) { q[3 * i] = queries.points[i].x; q[3 * i + 1] = queries.points[i].y; q[3 * i + 2] = queries.points[i].z; }
@@ -47,11 +52,16 @@ class DeviceKdTree {
     detail::check(sicp_knn(handle_.get(), q.data(), nullptr, nq, nullptr, k, tmp.data(), d2.data()), "nearestKSearchBatch");
     idx.assign(tmp.begin(), tmp.end());
   }
-  const detail::CloudHandle& handle() const { return handle_; }
+  const detail::CloudHandle& handle() const { ensure(); return handle_; }
 
  private:
+  void ensure() const {  // lazy upload (setInputCloudLazy) on the first use
+    if (handle_) return;
+    if (!cloud_) throw std::runtime_error("semanticicp (B200): DeviceKdTree used before setInputCloud");
+    handle_ = detail::upload_whole(*cloud_);
+  }
   PointCloudPtr cloud_;
-  detail::CloudHandle handle_;
+  mutable detail::CloudHandle handle_;
 };
 
 }  // namespace semanticicp

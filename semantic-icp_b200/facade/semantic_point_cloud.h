@@ -73,8 +73,11 @@ class SemanticPointCloud {
       detail::fill_matrices(rows, nc, first, covs.get());
       labeledCovariances[s] = covs;
       first += nc;
+      // the public per-class tree (semantic_point_cloud.h:39): registered LAZILY — its device upload happens on the first
+      // nearestKSearch, so a cloud that is only ever aligned (the PER_CLASS device cloud above already holds every class)
+      // is not uploaded a second time class by class
       KdTreePtr tree(new KdTree());
-      tree->setInputCloud(labeledPointClouds[s]);
+      tree->setInputCloudLazy(labeledPointClouds[s]);
       labeledKdTrees[s] = tree;
     }
   }
@@ -122,7 +125,7 @@ class SemanticPointCloud {
     sicp_cloud* c = nullptr;
     static const float zero3[3] = {0.f, 0.f, 0.f};
     static const std::uint32_t zero1 = 0;
-    detail::check(sicp_cloud_create(n ? xyz.data() : zero3, 12, n ? lab.data() : &zero1, 4, n, SICP_CLOUD_PER_CLASS, 0, &c), "semantic cloud upload");
+    detail::check(sicp_cloud_create(n ? xyz.data() : zero3, 12, n ? lab.data() : &zero1, 4, n, SICP_CLOUD_PER_CLASS, detail::device_index(), &c), "semantic cloud upload");
     device_ = detail::make_handle(c);
     detail::check(sicp_cloud_precompute(c, k_correspondences_, epsilon_, 0, nullptr), "semantic cloud covariances");
     return device_;

@@ -79,9 +79,17 @@ struct LabelOffset<pcl::PointXYZL> {
   static const void* get(const pcl::PointXYZL* p) { return p ? &p->label : nullptr; }
 };
 
+// GPU the facade objects of this process put their clouds on (one process per GPU: LOCAL_RANK, see shard.py).  The
+// reference has no notion of a device; semanticicp::setDevice() is the one extension a multi-GPU host needs.
+inline int& device_index() {
+  static int dev = 0;
+  return dev;
+}
+
 // Upload a PCL cloud (WHOLE layout): xyz read in place with the point stride, label (if the type has one) likewise.
 template <typename PointT>
-inline CloudHandle upload_whole(const pcl::PointCloud<PointT>& cloud, int device = 0) {
+inline CloudHandle upload_whole(const pcl::PointCloud<PointT>& cloud, int device = -1) {
+  if (device < 0) device = device_index();
   sicp_cloud* c = nullptr;
   const PointT* p0 = cloud.points.empty() ? nullptr : cloud.points.data();
   static PointT dummy;
@@ -102,5 +110,10 @@ inline void fill_matrices(const std::vector<double>& rows, std::size_t n, std::s
 }
 
 }  // namespace detail
+
+// Select the GPU for every facade object created afterwards (default 0).
+inline void setDevice(int device) { detail::device_index() = device; }
+inline int getDevice() { return detail::device_index(); }
+
 }  // namespace semanticicp
 #endif  // SICP_FACADE_COMPAT_H_

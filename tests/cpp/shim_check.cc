@@ -84,6 +84,21 @@ int main(int argc, char** argv) {
     { std::ofstream o(fn.c_str()); o << "# comment\nVERSION .7\nFIELDS x y z intensity label rgb\nSIZE 4 4 4 4 4 4\nTYPE F F F F U F\nCOUNT 1 1 1 1 1 1\nWIDTH 2\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS 2\nDATA ascii\n1 2 3 0.5 9 4.2e-38\n-4 5.5 6 0.25 11 0\n"; }
     CHECK(pcl::io::loadPCDFile(fn, b) == 0 && b.size() == 2 && b[1].x == -4.f && b[1].y == 5.5f && b[0].label == 9 && b[1].label == 11, "foreign header with extra fields");
     CHECK(pcl::io::loadPCDFile(dir + "/does_not_exist.pcd", b) == -1, "missing file");
+    // malformed / hostile headers must fail with -1: no out-of-bounds read, no giant allocation, no exception
+    const char* bad_headers[] = {
+        "FIELDS x y z\nSIZE 2 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n0123456789",          // TYPE F with SIZE 2
+        "FIELDS x y z\nSIZE 4 4 3\nTYPE F F U\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n01234567890123",      // TYPE U with SIZE 3
+        "FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 -3 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n012345678901",       // negative COUNT
+        "FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 0 1\nWIDTH 1\nHEIGHT 1\nPOINTS 1\nDATA binary\n012345678901",        // zero COUNT
+        "FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 4000000000000\nDATA binary\n0123456", // POINTS beyond the file
+        "FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 1\nHEIGHT 1\nPOINTS 900000000000\nDATA ascii\n1 2 3\n",   // ... in ascii too
+        "FIELDS x y z\nSIZE 4 4 4\nTYPE F F F\nCOUNT 1 1 1\nWIDTH 3\nHEIGHT 1\nPOINTS 3\nDATA binary\n0123456789012345678",  // truncated data
+    };
+    for (std::size_t i = 0; i < sizeof bad_headers / sizeof bad_headers[0]; i++) {
+      const std::string bf = dir + "/bad.pcd";
+      { std::ofstream o(bf.c_str(), std::ios::binary); o << bad_headers[i]; }
+      CHECK(pcl::io::loadPCDFile(bf, b) == -1, "malformed header rejected");
+    }
   }
   // default-constructed pose is the identity (GICP::align(finalCloud) relies on it)
   const double id[7] = {0, 0, 0, 1, 0, 0, 0};

@@ -36,6 +36,52 @@ def test_config2_kitti_full_size_em_parity(sicp, oracle, pkg, kitti_full):
     assert list(res["pass_lm_iters"]) == list(ref["pass_lm_iters"])
 
 
+def test_config2_pass_result_is_a_stationary_point_scipy(sicp, pkg):
+    """Independent check of the M-step (not the oracle, not Ceres' rules): the pose a pass ends with must be a minimiser of
+    that pass's effective objective  1/2 sum_i w_i * 9 log(1 + sqrt(r_i^2 + eps)/9),  r_i = d^T (C_t + R C_s R^T)^-1 d
+    (SURVEY.md Appendix B.2), built here in numpy from explicit 3x3 covariances and inverses over the GPU's own
+    correspondences of that pass.  scipy.optimize.least_squares restarted AT that pose must not move it."""
+    from scipy.optimize import least_squares
+    from scipy.spatial.transform import Rotation
+
+    p = pkg.synth.kitti_pair(pair=0, n_points=60_000)  # 240,000 residual slots: the numpy objective stays within seconds
+    src, tgt, opts = _em(sicp, p)
+    res = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
+    n = res["outer_iter"]
+    before = res["pass_pose"][n - 2] if n >= 2 else p["init"]
+    after = res["pass_pose"][n - 1]
+    idx, w, d2 = sicp.correspondences(sicp.ALGO_EM, src, tgt, opts, before)  # correspondences + E-step weights of the last pass
+    keep = (idx >= 0) & (w > 0)
+    si, ci = np.nonzero(keep)
+    ti, ww = idx[si, ci], w[si, ci]
+    eps = 1e-3
+    ns, nt = src.normals()[si], tgt.normals()[ti]
+    eye = np.eye(3)[None]
+    Cs = eye - (1 - eps) * ns[:, :, None] * ns[:, None, :]
+    Ct = eye - (1 - eps) * nt[:, :, None] * nt[:, None, :]
+    ps, pt = p["src_xyz"][si].astype(np.float64), p["tgt_xyz"][ti].astype(np.float64)
+    R0 = Rotation.from_quat(after[:4]).as_matrix()
+    t0 = after[4:]
+
+    def residuals(delta):  # T = T_after * exp(delta) with delta = (upsilon, omega)  (local_parameterization_se3.h:22)
+        dR = Rotation.from_rotvec(delta[3:]).as_matrix()
+        om = delta[3:]
+        th = np.linalg.norm(om)
+        O = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0.0]])
+        V = np.eye(3) + 0.5 * O + O @ O / 6.0 if th < 1e-6 else np.eye(3) + (1 - np.cos(th)) / th**2 * O + (th - np.sin(th)) / th**3 * (O @ O)
+        R, t = R0 @ dR, t0 + R0 @ (V @ delta[:3])
+        d = pt - (ps @ R.T + t)
+        M = np.linalg.inv(Ct + np.einsum("ij,njk,lk->nil", R, Cs, R))
+        r = np.einsum("ni,nij,nj->n", d, M, d)
+        rho = ww * 9.0 * np.log1p(np.sqrt(r * r + np.finfo(float).eps) / 9.0)  # ScaledLoss(Cauchy(3), w) o SQLoss
+        return np.sqrt(rho)
+
+    f0 = residuals(np.zeros(6))
+    sol = least_squares(residuals, np.zeros(6), method="trf", jac="2-point", x_scale=1.0, xtol=1e-12, ftol=1e-15, gtol=1e-15, max_nfev=12)
+    assert np.linalg.norm(sol.x[3:]) < 0.3 * ROT_TOL and np.linalg.norm(sol.x[:3]) < 0.3 * TRANS_TOL, sol.x
+    assert 0.5 * (f0 @ f0) - sol.cost <= 1e-9 * 0.5 * (f0 @ f0)
+
+
 @pytest.mark.parametrize("k", [1, 4, 20])
 def test_config2_knn_full_size_bit_exact_and_sorted(sicp, oracle, kitti_full, k):
     p = kitti_full
