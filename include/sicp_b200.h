@@ -188,6 +188,18 @@ sicp_status sicp_pose_errors(size_t n, const double* gt7s, const double* est7s, 
 sicp_status sicp_filter_range(const void* xyz, size_t xyz_stride, size_t n, double range, int device, uint32_t* keep_idx_out,
                               size_t* n_keep_out);
 
+/* ---- fusing per-class pose estimates (dead code in the reference, kept for completeness) ------------
+ * SemanticIterativeClosestPoint::iterativeMean (impl/semantic_icp.hpp:169-191): Karcher mean of n poses on SE(3), started at
+ * poses7[0], at most max_iterations steps, stopping when |log(new^-1 * old)|^2 < 0.01.  *converged (nullable) = 0 when the
+ * step limit was hit ("Iterative Mean Failed"); out7 is the last iterate either way. */
+sicp_status sicp_iterative_mean(size_t n, const double* poses7, int max_iterations, double* out7, int* converged);
+/* SemanticIterativeClosestPoint::poseFusion (impl/semantic_icp.hpp:193-265): minimise sum_n Huber_10((e_n^T W_n e_n)^2) with
+ * e_n = log(T * pose_n^-1), W_n = cov_n^-1 * (mean det cov)^(1/6), by LM from init7 (50,000 iterations, tolerances
+ * 1e-4 * Sophus epsilon).  covs36: n row-major 6x6 matrices (translation block first, Sophus tangent order).  A single
+ * pose is returned unchanged. */
+sicp_status sicp_pose_fusion(size_t n, const double* poses7, const double* covs36, const double* init7, double* out7,
+                             int* lm_iterations);
+
 #ifdef __cplusplus
 }
 #endif

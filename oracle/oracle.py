@@ -296,3 +296,22 @@ def filter_range(xyz, rng):
     xyz = _f32(xyz)
     r2 = (xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2]
     return np.nonzero(~(r2.astype(np.float64) > rng * rng))[0].astype(np.uint32)
+
+
+def iterative_mean(poses7, max_iterations=100):
+    """SemanticIterativeClosestPoint::iterativeMean (impl/semantic_icp.hpp:169-191): (mean pose7, converged)."""
+    p = _f64(np.asarray(poses7).reshape(-1, 7))
+    out = np.zeros(7)
+    conv = C.c_int(0)
+    lib().orc_iterative_mean(_p(p), C.c_int(len(p)), C.c_int(max_iterations), _p(out), C.byref(conv))
+    return out, bool(conv.value)
+
+
+def pose_fusion(poses7, covs, init7):
+    """SemanticIterativeClosestPoint::poseFusion (impl/semantic_icp.hpp:193-265): (fused pose7, LM iterations)."""
+    p = _f64(np.asarray(poses7).reshape(-1, 7))
+    c = _f64(np.asarray(covs).reshape(-1, 36))
+    out = np.zeros(7)
+    it = C.c_int(0)
+    lib().orc_pose_fusion(_p(p), _p(c), C.c_int(len(p)), _p(_f64(init7)), _p(out), C.byref(it))
+    return out, it.value

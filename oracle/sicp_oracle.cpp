@@ -691,16 +691,17 @@ static bool chol_solve6(const double A[6][6], const double* b, double* x) {
 struct LMStats { int iterations = 0, successful = 0, termination = 0; double initial_cost = 0, final_cost = 0; };
 enum { TERM_NO_CONV = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_RADIUS = 4, TERM_FAIL = 5, TERM_EMPTY = 6 };
 
-static LMStats lm_solve(const Problem& P, SE3* x, int threads) {
+// The Ceres-style trust-region loop over ONE SE(3) block, generic in the evaluation callback
+//   eval(T, want_jacobian, &E): E.cost = 1/2 sum rho, and with want_jacobian E.g = J^T r, E.H = J^T J (loss-corrected, 6-dof)
+template <class EvalFn>
+static LMStats lm_solve_fn(EvalFn&& eval, SE3* x, double gtol, double ftol, int max_iter) {
   LMStats st;
-  if (P.res.empty()) { st.termination = TERM_EMPTY; return st; }  // Ceres: nothing to optimise, pose unchanged
-  const double gtol = 0.1 * kSophusEps, ftol = 0.1 * kSophusEps, ptol = 1e-8;  // gicp.hpp:139-140
-  const int max_iter = 400;                                                      // gicp.hpp:143
+  const double ptol = 1e-8;
   const double min_rel_decrease = 1e-3, max_radius = 1e16, min_radius = 1e-32, min_diag = 1e-6, max_diag = 1e32;
   double radius = 1e4, decrease_factor = 2.0;
   bool reuse_diag = false;
   Eval E;
-  evaluate(P, *x, true, &E, threads);
+  eval(*x, true, &E);
   st.initial_cost = E.cost;
   double scale[6];
   for (int j = 0; j < 6; j++) scale[j] = 1.0 / (1.0 + std::sqrt(E.H[j][j]));
@@ -750,7 +751,7 @@ static LMStats lm_solve(const Problem& P, SE3* x, int threads) {
     for (int j = 0; j < 6; j++) delta[j] = step[j] * scale[j];
     SE3 cand = se3_plus(*x, delta);
     Eval Ec;
-    evaluate(P, cand, false, &Ec, threads);
+    eval(cand, false, &Ec);
     double a7[7], b7[7]; se3_to7(*x, a7); se3_to7(cand, b7);
     double sn = 0; for (int i = 0; i < 7; i++) sn += (a7[i] - b7[i]) * (a7[i] - b7[i]);
     sn = std::sqrt(sn);
@@ -760,7 +761,7 @@ static LMStats lm_solve(const Problem& P, SE3* x, int threads) {
     double rel = cost_change / model;
     if (rel > min_rel_decrease) {
       *x = cand; x_norm = norm7(*x);
-      evaluate(P, *x, true, &E, threads);
+      eval(*x, true, &E);
       cost = E.cost;
       gmax = grad_max_norm(*x, E.g);
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3));
@@ -773,6 +774,117 @@ static LMStats lm_solve(const Problem& P, SE3* x, int threads) {
   st.iterations = iter;
   st.final_cost = cost;
   return st;
+}
+static LMStats lm_solve(const Problem& P, SE3* x, int threads) {
+  if (P.res.empty()) { LMStats st; st.termination = TERM_EMPTY; return st; }  // Ceres: nothing to optimise, pose unchanged
+  // gicp.hpp:139-143: gradient / function tolerance 0.1 * Sophus epsilon, 400 iterations
+  return lm_solve_fn([&](const SE3& T, bool jac, Eval* E) { evaluate(P, T, jac, E, threads); }, x, 0.1 * kSophusEps, 0.1 * kSophusEps, 400);
+}
+
+// ------------------------------------------------------------------ pose averaging / fusion (impl/semantic_icp.hpp:169-265)
+static SE3 iterative_mean(const std::vector<SE3>& in, size_t max_iterations, bool* converged) {
+  SE3 avg = in.front();
+  const double w = 1.0 / (double)in.size();
+  *converged = false;
+  for (size_t i = 0; i < max_iterations; i++) {
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    const SE3 inv = se3_inv(avg);
+    for (const SE3& T : in) {
+      double l[6];
+      se3_log(se3_mul(inv, T), l);
+      for (int c = 0; c < 6; c++) a[c] += w * l[c];
+    }
+    SE3 nxt = se3_mul(avg, se3_exp(a));
+    double d[6], sq = 0;
+    se3_log(se3_mul(se3_inv(nxt), avg), d);
+    for (int c = 0; c < 6; c++) sq += d[c] * d[c];
+    avg = nxt;
+    if (sq < 0.01) { *converged = true; return avg; }  // semantic_icp.hpp:184-185
+  }
+  return avg;  // "Iterative Mean Failed" (semantic_icp.hpp:189-190)
+}
+static bool inv6(const double* A, double* out) {
+  double M[6][12];
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) { M[r][c] = A[6 * r + c]; M[r][6 + c] = r == c ? 1.0 : 0.0; }
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++) if (std::fabs(M[r][k]) > std::fabs(M[piv][k])) piv = r;
+    if (!(std::fabs(M[piv][k]) > 0)) return false;
+    if (piv != k) for (int c = 0; c < 12; c++) std::swap(M[k][c], M[piv][c]);
+    const double d = M[k][k];
+    for (int c = 0; c < 12; c++) M[k][c] /= d;
+    for (int r = 0; r < 6; r++) if (r != k) { const double f = M[r][k]; if (f != 0) for (int c = 0; c < 12; c++) M[r][c] -= f * M[k][c]; }
+  }
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) out[6 * r + c] = M[r][6 + c];
+  return true;
+}
+static double det6(const double* A) {
+  double M[6][6];
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) M[r][c] = A[6 * r + c];
+  double det = 1.0;
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++) if (std::fabs(M[r][k]) > std::fabs(M[piv][k])) piv = r;
+    if (M[piv][k] == 0) return 0.0;
+    if (piv != k) { for (int c = 0; c < 6; c++) std::swap(M[k][c], M[piv][c]); det = -det; }
+    det *= M[k][k];
+    for (int r = k + 1; r < 6; r++) { const double f = M[r][k] / M[k][k]; for (int c = k; c < 6; c++) M[r][c] -= f * M[k][c]; }
+  }
+  return det;
+}
+// PoseFusionCostFunctor (semantic_icp.hpp:193-211): r = e^T W e, e = log(T * pose^-1); HuberLoss(10) on r^2
+static double fusion_residual(const SE3& T, const SE3& pinv, const double* W) {
+  double e[6];
+  se3_log(se3_mul(T, pinv), e);
+  double r = 0;
+  for (int a = 0; a < 6; a++) { double s = 0; for (int b = 0; b < 6; b++) s += W[6 * a + b] * e[b]; r += e[a] * s; }
+  return r;
+}
+static SE3 pose_fusion(const std::vector<SE3>& poses, const std::vector<double>& covs36, const SE3& init, int* lm_iters) {
+  *lm_iters = 0;
+  if (poses.size() == 1) return poses[0];
+  const size_t n = poses.size();
+  double det = 0;
+  for (size_t i = 0; i < n; i++) det += det6(&covs36[36 * i]) / (double)n;
+  const double scale = 1.0 / std::pow(1.0 / det, 1.0 / 6.0);
+  std::vector<SE3> pinv(n);
+  std::vector<double> W(36 * n);
+  for (size_t i = 0; i < n; i++) {
+    pinv[i] = se3_inv(poses[i]);
+    inv6(&covs36[36 * i], &W[36 * i]);
+    for (int k = 0; k < 36; k++) W[36 * i + k] *= scale;
+  }
+  SE3 x = init;
+  const double h = 1e-6;  // the reference differentiates r(T * exp(delta)) automatically; central differences stand in for it
+  auto eval = [&](const SE3& T, bool jac, Eval* E) {
+    std::memset(E, 0, sizeof *E);
+    for (size_t i = 0; i < n; i++) {
+      const double r = fusion_residual(T, pinv[i], &W[36 * i]);
+      const double s2 = r * r;
+      const double rho0 = s2 <= 100.0 ? s2 : 20.0 * std::sqrt(s2) - 100.0;                                           // HuberLoss(10.0)
+      const double rho1 = s2 <= 100.0 ? 1.0 : std::max(std::numeric_limits<double>::min(), 10.0 / std::sqrt(s2));
+      E->cost += 0.5 * rho0;
+      if (!jac) continue;
+      double j[6];
+      for (int k = 0; k < 6; k++) {
+        double d[6] = {0, 0, 0, 0, 0, 0};
+        d[k] = h;
+        const double rp = fusion_residual(se3_plus(T, d), pinv[i], &W[36 * i]);
+        d[k] = -h;
+        const double rm = fusion_residual(se3_plus(T, d), pinv[i], &W[36 * i]);
+        j[k] = (rp - rm) / (2.0 * h);
+      }
+      for (int a = 0; a < 6; a++) {
+        E->g[a] += rho1 * j[a] * r;
+        for (int b = 0; b <= a; b++) E->H[a][b] += rho1 * j[a] * j[b];
+      }
+    }
+    for (int a = 0; a < 6; a++) for (int b = 0; b < a; b++) E->H[b][a] = E->H[a][b];
+  };
+  // semantic_icp.hpp:255-260: 50,000 iterations, gradient / function tolerance 1e-4 * Sophus epsilon
+  LMStats st = lm_solve_fn(eval, &x, 0.0001 * kSophusEps, 0.0001 * kSophusEps, 50000);
+  *lm_iters = st.iterations;
+  return x;
 }
 
 }  // namespace orc
@@ -797,6 +909,20 @@ struct orc_trace {      // optional per-pass trace (arrays sized by caller: max_
 struct orc_result { double pose7[7]; int outer_iter; int lm_iters_total; double final_cost; int n_corr_last; double seconds; };
 
 void orc_set_search_threads(int t) { g_search_threads = t; }
+
+void orc_iterative_mean(const double* poses7, int n, int max_iterations, double* out7, int* converged) {
+  std::vector<SE3> in(n);
+  for (int i = 0; i < n; i++) in[i] = se3_from7(poses7 + 7 * i);
+  bool ok = false;
+  se3_to7(iterative_mean(in, (size_t)max_iterations, &ok), out7);
+  *converged = ok ? 1 : 0;
+}
+void orc_pose_fusion(const double* poses7, const double* covs36, int n, const double* init7, double* out7, int* lm_iters) {
+  std::vector<SE3> in(n);
+  for (int i = 0; i < n; i++) in[i] = se3_from7(poses7 + 7 * i);
+  std::vector<double> covs(covs36, covs36 + 36 * (size_t)n);
+  se3_to7(pose_fusion(in, covs, se3_from7(init7), lm_iters), out7);
+}
 
 int orc_num_threads() {
 #ifdef _OPENMP

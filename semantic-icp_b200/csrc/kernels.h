@@ -32,6 +32,7 @@ struct LMConfig {
   double mse_stop;       // 1e-5 (GICP, EM) / 1e-3 (SEMANTIC)
   int outer_cap;         // 50 / 35
   int variant;           // shape of the LM kernel (lm.cu: kLmShapes)
+  int ctl_share8;        // sweep share of the LM controller block in eighths of a normal block's share (0..8)
 };
 constexpr int kLmVariants = 2;
 constexpr int kLmMaxGrid = 320;       // block partials reserved per workspace
@@ -72,5 +73,10 @@ sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const ch
 // fused labels (impl/em_icp.hpp:202-268)
 sicp_status launch_fused_labels(const sicp_cloud* src, const sicp_cloud* tgt, double eps, double gate_d2, const double* d_pose7, const int* d_corr,
                                 const float* d_d2, uint32_t* d_labels_out, cudaStream_t st);
+
+// pose averaging / fusion of per-class estimates (impl/semantic_icp.hpp:169-265)
+sicp_status launch_iterative_mean(const double* d_poses7, int n, int max_iter, double* d_out7, int* d_converged, cudaStream_t st);
+sicp_status launch_pose_fusion(const double* d_pinv7s, const double* d_Ws, int n, const double* d_init7, int max_iter, double* d_out7, int* d_iters,
+                               cudaStream_t st);
 
 }  // namespace sicp

@@ -340,8 +340,9 @@ __device__ __forceinline__ double norm7(const double* a) {
 // scaled Gauss-Newton system (formed in registers), of the Cholesky factor and of the triangular solves (pivots and
 // solution components travel by shuffle); the model decrease is a 6-lane dot product.  State goes back to shared
 // memory once, at the end.
-__device__ __forceinline__ void lm_control_warp(LMState& S, const double* tot, int max_iter, double* s_L, int lane) {
-  const double ftol = 0.1 * kSophusEps, gtol = 0.1 * kSophusEps, ptol = 1e-8;
+__device__ __forceinline__ void lm_control_warp(LMState& S, const double* tot, int max_iter, double* s_L, int lane,
+                                                const double ftol = 0.1 * kSophusEps, const double gtol = 0.1 * kSophusEps) {
+  const double ptol = 1e-8;
   const int i = lane < 6 ? lane : 0;  // lanes >= 6 shadow row 0; nothing is ever read from them
   // ---- state -> registers
   double x[7], cand[7], scale[6], Hrow[6];
@@ -587,7 +588,12 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
   // Work split: a block owns a contiguous range of groups and deals them to its warps round-robin, so the four
   // schedulers of an SM carry the same number of groups (+-1).
   const int ngroups = a.sv.nslots >> 5;
-  const int g0 = (int)(((long long)ngroups * blockIdx.x) / gridDim.x), g1 = (int)(((long long)ngroups * (blockIdx.x + 1)) / gridDim.x);
+  // The controller block (block 0) takes ctl_share / 8 of a normal share (0 = it does not sweep): it then never is the
+  // late arrival it would itself be waiting for, which shortens the serial reduce-decide-publish section between sweeps.
+  const long long units = 8ll * (gridDim.x - 1) + a.cfg.ctl_share8;  // eighths of a share
+  const long long u0 = blockIdx.x == 0 ? 0 : a.cfg.ctl_share8 + 8ll * (blockIdx.x - 1);
+  const long long u1 = blockIdx.x == 0 ? a.cfg.ctl_share8 : u0 + 8;
+  const int g0 = (int)(((long long)ngroups * u0) / units), g1 = (int)(((long long)ngroups * u1) / units);
   const int lane = threadIdx.x & 31;
   const int gfirst = g0 + (threadIdx.x >> 5);
   if (gfirst >= g1) return;
@@ -936,6 +942,118 @@ __global__ void fused_labels_kernel(CloudView sv, CloudView tv, double eps, doub
   labels_out[o] = (uint32_t)(best_s + 1);
 }
 
+// ------------------------------------------------------------------ pose averaging / fusion (impl/semantic_icp.hpp:169-265)
+// SemanticIterativeClosestPoint::iterativeMean: Karcher mean on SE(3).  One warp; the lanes take the logarithms of
+// tAverage^-1 * T_j, lane 0 adds them in index order (the reference's summation order) and steps the mean.
+__global__ void iterative_mean_kernel(const double* __restrict__ poses7, int n, int max_iter, double* __restrict__ out7, int* __restrict__ converged) {
+  extern __shared__ double s_log[];  // [n][6]
+  __shared__ double s_avg[7];
+  __shared__ int s_done;
+  const int lane = threadIdx.x;
+  if (lane < 7) s_avg[lane] = poses7[lane];  // tAverage = in.front()
+  if (lane == 0) s_done = 0;
+  __syncwarp();
+  const double w = 1.0 / (double)n;
+  for (int it = 0; it < max_iter; it++) {
+    const Pose inv = pose_inv(pose_from7(s_avg));
+    for (int j = lane; j < n; j += 32) pose_log(pose_mul(inv, pose_from7(poses7 + 7 * (size_t)j)), s_log + 6 * (size_t)j);
+    __syncwarp();
+    if (lane == 0) {
+      double avg[6] = {0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < n; j++)
+        for (int c = 0; c < 6; c++) avg[c] += w * s_log[6 * (size_t)j + c];
+      const Pose cur = pose_from7(s_avg);
+      const Pose nxt = pose_mul(cur, pose_exp(avg));
+      double d[6], sq = 0;
+      pose_log(pose_mul(pose_inv(nxt), cur), d);
+      for (int c = 0; c < 6; c++) sq += d[c] * d[c];
+      pose_to7(nxt, s_avg);
+      if (sq < 0.01) s_done = 1;  // semantic_icp.hpp:184
+    }
+    __syncwarp();
+    if (s_done) break;
+  }
+  // on failure the reference returns the average of the second-to-last step... no: `tAverage = newTAverage` every
+  // iteration, so the value after the last step is what it returns either way (semantic_icp.hpp:187-190)
+  if (lane < 7) out7[lane] = s_avg[lane];
+  if (lane == 0) *converged = s_done;
+}
+
+// SemanticIterativeClosestPoint::poseFusion: minimise  1/2 sum_n Huber_10( r_n^2 ),  r_n = e_n^T W_n e_n,
+// e_n = log(T * pose_n^-1),  W_n = cov_n^-1 * scale, over T with the SE(3) local parameterisation, by the same
+// Ceres-style LM controller as the registration M-step (tolerances 1e-4 * Sophus epsilon, 50,000 iterations).
+// One warp: lane n owns residual block n (blocks beyond 32 are strided).  The 6-dof Jacobian of the scalar residual is
+// taken by central differences of r(T * exp(h e_k)) — the reference differentiates the same function automatically.
+__device__ __forceinline__ double fusion_residual(const Pose& T, const double* pinv7, const double* W) {
+  double e[6];
+  pose_log(pose_mul(T, pose_from7(pinv7)), e);
+  double r = 0;
+  for (int a = 0; a < 6; a++) {
+    double s = 0;
+    for (int b = 0; b < 6; b++) s += W[6 * a + b] * e[b];
+    r += e[a] * s;
+  }
+  return r;
+}
+__global__ void pose_fusion_kernel(const double* __restrict__ pinv7s, const double* __restrict__ Ws, int n, const double* __restrict__ init7,
+                                   int max_iter, double* __restrict__ out7, int* __restrict__ iters_out) {
+  __shared__ LMState S;
+  __shared__ double s_tot[kAcc];
+  __shared__ double s_L[36];
+  __shared__ double s_pose[7];
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    double* ss = reinterpret_cast<double*>(&S);
+    for (int i = 0; i < (int)(sizeof(LMState) / sizeof(double)); i++) ss[i] = 0.0;
+    for (int i = 0; i < 7; i++) { S.x[i] = init7[i]; s_pose[i] = init7[i]; }
+  }
+  __syncwarp();
+  const double h = 1e-6, huber_a = 10.0, huber_b = 100.0;
+  for (;;) {
+    const Pose T = pose_from7(s_pose);
+    double acc[kAcc];
+#pragma unroll
+    for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
+    for (int b = lane; b < n; b += 32) {
+      const double* pi = pinv7s + 7 * (size_t)b;
+      const double* W = Ws + 36 * (size_t)b;
+      const double r = fusion_residual(T, pi, W);
+      double j[6];
+      for (int k = 0; k < 6; k++) {
+        double d[6] = {0, 0, 0, 0, 0, 0};
+        d[k] = h;
+        const double rp = fusion_residual(pose_plus(T, d), pi, W);
+        d[k] = -h;
+        const double rm = fusion_residual(pose_plus(T, d), pi, W);
+        j[k] = (rp - rm) / (2.0 * h);
+      }
+      // HuberLoss(10): rho(s) = s (s <= 100) | 20 sqrt(s) - 100; rho'' <= 0, so Ceres scales residual and Jacobian by sqrt(rho')
+      const double s2 = r * r;
+      const double rho0 = s2 <= huber_b ? s2 : 2.0 * huber_a * sqrt(s2) - huber_b;
+      const double rho1 = s2 <= huber_b ? 1.0 : fmax(DBL_MIN, huber_a / sqrt(s2));
+      int q = 0;
+      for (int a = 0; a < 6; a++) {
+        for (int c = 0; c <= a; c++) acc[q++] += rho1 * j[a] * j[c];
+        acc[21 + a] += rho1 * j[a] * r;
+      }
+      acc[27] += 0.5 * rho0;
+    }
+#pragma unroll
+    for (int i = 0; i < kAcc; i++) {  // fixed-order butterfly: deterministic
+      double v = acc[i];
+      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(kFullMask, v, off);
+      if (lane == 0) s_tot[i] = v;
+    }
+    __syncwarp();
+    lm_control_warp(S, s_tot, max_iter, s_L, lane, 0.0001 * kSophusEps, 0.0001 * kSophusEps);
+    if (lane < 7) s_pose[lane] = S.cand[lane];
+    __syncwarp();
+    if (S.done) break;
+  }
+  if (lane < 7) out7[lane] = S.x[lane];
+  if (lane == 0) *iters_out = S.iter;
+}
+
 // ------------------------------------------------------------------ host launchers
 // Shapes of the LM kernel (LMConfig.variant).  0 is the lone-registration shape: one 256-thread CTA per SM with every
 // record chain of a slot interleaved (~240 registers).  The others trade per-solve speed for co-residency: a CTA that
@@ -1002,6 +1120,7 @@ static sicp_status launch_lm_args(LMArgs& args, int grid, cudaStream_t st) {
   SICP_CUDA(cudaGetDevice(&dev));
   grid = std::max(1, std::min(grid, lm_max_grid(dev, args.cfg.algo, variant)));  // also sets the shared-memory attribute
   args.partials = reinterpret_cast<double*>(args.sync) + kLmSyncDoubles;
+  if (grid == 1 || args.cfg.ctl_share8 < 0 || args.cfg.ctl_share8 > 8) args.cfg.ctl_share8 = 8;  // a lone block sweeps everything
   void* params[] = {&args};
   SICP_CUDA(cudaLaunchCooperativeKernel(lm_entry(args.cfg.algo, variant), dim3(grid), dim3(kLmShapes[variant].threads), params, lm_smem(args.cfg.algo, variant), st));
   count_launches(1);
@@ -1028,6 +1147,20 @@ sicp_status launch_fused_labels(const sicp_cloud* src, const sicp_cloud* tgt, do
                                 const float* d_d2, uint32_t* d_labels_out, cudaStream_t st) {
   if (src->nslots == 0) return SICP_OK;
   fused_labels_kernel<<<(src->nslots + 127) / 128, 128, 0, st>>>(src->view(), tgt->view(), eps, gate_d2, d_pose7, d_corr, d_d2, d_labels_out);
+  count_launches(1);
+  SICP_CUDA(cudaGetLastError());
+  return SICP_OK;
+}
+
+sicp_status launch_iterative_mean(const double* d_poses7, int n, int max_iter, double* d_out7, int* d_converged, cudaStream_t st) {
+  iterative_mean_kernel<<<1, 32, sizeof(double) * 6 * (size_t)n, st>>>(d_poses7, n, max_iter, d_out7, d_converged);
+  count_launches(1);
+  SICP_CUDA(cudaGetLastError());
+  return SICP_OK;
+}
+sicp_status launch_pose_fusion(const double* d_pinv7s, const double* d_Ws, int n, const double* d_init7, int max_iter, double* d_out7, int* d_iters,
+                               cudaStream_t st) {
+  pose_fusion_kernel<<<1, 32, 0, st>>>(d_pinv7s, d_Ws, n, d_init7, max_iter, d_out7, d_iters);
   count_launches(1);
   SICP_CUDA(cudaGetLastError());
   return SICP_OK;

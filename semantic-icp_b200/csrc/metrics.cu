@@ -5,6 +5,7 @@
 // They reuse the exact kNN of knn_cov.cu (K2) and the SE(3) arithmetic of se3.cuh.
 #include <cub/device/device_select.cuh>
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -165,6 +166,108 @@ sicp_status sicp_pose_errors(size_t n, const double* gt7s, const double* est7s, 
   if (d_est) cudaFreeAsync(d_est, st);
   if (d_err) cudaFreeAsync(d_err, st);
   return rc;
+}
+
+// 6x6 inverse by Gauss-Jordan with partial pivoting (host; pose covariances are tiny); false when singular
+static bool inv6(const double* A, double* out) {
+  double M[6][12];
+  for (int r = 0; r < 6; r++)
+    for (int c = 0; c < 6; c++) { M[r][c] = A[6 * r + c]; M[r][6 + c] = r == c ? 1.0 : 0.0; }
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++) if (std::fabs(M[r][k]) > std::fabs(M[piv][k])) piv = r;
+    if (!(std::fabs(M[piv][k]) > 0)) return false;
+    if (piv != k) for (int c = 0; c < 12; c++) std::swap(M[k][c], M[piv][c]);
+    const double d = M[k][k];
+    for (int c = 0; c < 12; c++) M[k][c] /= d;
+    for (int r = 0; r < 6; r++)
+      if (r != k) { const double f = M[r][k]; if (f != 0) for (int c = 0; c < 12; c++) M[r][c] -= f * M[k][c]; }
+  }
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) out[6 * r + c] = M[r][6 + c];
+  return true;
+}
+static double det6(const double* A) {  // LU with partial pivoting
+  double M[6][6];
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) M[r][c] = A[6 * r + c];
+  double det = 1.0;
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    for (int r = k + 1; r < 6; r++) if (std::fabs(M[r][k]) > std::fabs(M[piv][k])) piv = r;
+    if (M[piv][k] == 0) return 0.0;
+    if (piv != k) { for (int c = 0; c < 6; c++) std::swap(M[k][c], M[piv][c]); det = -det; }
+    det *= M[k][k];
+    for (int r = k + 1; r < 6; r++) { const double f = M[r][k] / M[k][k]; for (int c = k; c < 6; c++) M[r][c] -= f * M[k][c]; }
+  }
+  return det;
+}
+
+sicp_status sicp_iterative_mean(size_t n, const double* poses7, int max_iterations, double* out7, int* converged) {
+  SICP_REQUIRE(poses7 && out7 && n >= 1, "null argument or empty pose list");
+  SICP_REQUIRE(n <= 4096, "at most 4096 poses");
+  for (size_t i = 0; i < n; i++) SICP_CHECK(validate_pose7(poses7 + 7 * i, "sicp_iterative_mean"));
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { set_error("no CUDA device available (libsicp_b200 has no CPU fallback)"); return SICP_ERR_CUDA; }
+  cudaStream_t st = current_stream();
+  double *d_in = nullptr, *d_out = nullptr;
+  double h_out[8];
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMallocAsync(&d_in, 56 * n, st));
+    SICP_CUDA(cudaMallocAsync(&d_out, 64, st));
+    SICP_CUDA(cudaMemcpyAsync(d_in, poses7, 56 * n, cudaMemcpyHostToDevice, st));
+    SICP_CHECK(launch_iterative_mean(d_in, (int)n, max_iterations, d_out, reinterpret_cast<int*>(d_out + 7), st));
+    SICP_CUDA(cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    return SICP_OK;
+  };
+  const sicp_status rc = body();
+  if (d_in) cudaFreeAsync(d_in, st);
+  if (d_out) cudaFreeAsync(d_out, st);
+  SICP_CHECK(rc);
+  std::memcpy(out7, h_out, 56);
+  if (converged) std::memcpy(converged, h_out + 7, sizeof(int));
+  return SICP_OK;
+}
+
+sicp_status sicp_pose_fusion(size_t n, const double* poses7, const double* covs36, const double* init7, double* out7, int* lm_iterations) {
+  SICP_REQUIRE(poses7 && covs36 && init7 && out7 && n >= 1, "null argument or empty pose list");
+  SICP_REQUIRE(n <= 4096, "at most 4096 poses");
+  for (size_t i = 0; i < n; i++) SICP_CHECK(validate_pose7(poses7 + 7 * i, "sicp_pose_fusion"));
+  SICP_CHECK(validate_pose7(init7, "sicp_pose_fusion (init7)"));
+  if (lm_iterations) *lm_iterations = 0;
+  if (n == 1) { std::memcpy(out7, poses7, 56); return SICP_OK; }  // semantic_icp.hpp:223-224
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt == 0) { set_error("no CUDA device available (libsicp_b200 has no CPU fallback)"); return SICP_ERR_CUDA; }
+  // scale = (mean determinant)^(1/6) (semantic_icp.hpp:232-237: 1 / pow(1/det, 1/6)); W_n = cov_n^-1 * scale; pose_n^-1
+  double det = 0;
+  for (size_t i = 0; i < n; i++) det += det6(covs36 + 36 * i) / (double)n;
+  const double scale = 1.0 / std::pow(1.0 / det, 1.0 / 6.0);
+  std::vector<double> h(43 * n);  // [n][7] inverse poses, then [n][36] weights
+  for (size_t i = 0; i < n; i++) {
+    pose_to7(pose_inv(pose_from7(poses7 + 7 * i)), &h[7 * i]);
+    double* W = &h[7 * n + 36 * i];
+    SICP_REQUIRE(inv6(covs36 + 36 * i, W), "singular pose covariance");
+    for (int k = 0; k < 36; k++) W[k] *= scale;
+  }
+  cudaStream_t st = current_stream();
+  double *d_in = nullptr, *d_out = nullptr;
+  double h_out[8];
+  auto body = [&]() -> sicp_status {
+    SICP_CUDA(cudaMallocAsync(&d_in, sizeof(double) * (43 * n + 7), st));
+    SICP_CUDA(cudaMallocAsync(&d_out, 64, st));
+    SICP_CUDA(cudaMemcpyAsync(d_in, h.data(), sizeof(double) * 43 * n, cudaMemcpyHostToDevice, st));
+    SICP_CUDA(cudaMemcpyAsync(d_in + 43 * n, init7, 56, cudaMemcpyHostToDevice, st));
+    SICP_CHECK(launch_pose_fusion(d_in, d_in + 7 * n, (int)n, d_in + 43 * n, 50000, d_out, reinterpret_cast<int*>(d_out + 7), st));  // max_num_iterations, semantic_icp.hpp:257
+    SICP_CUDA(cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, st));
+    SICP_CUDA(cudaStreamSynchronize(st));
+    return SICP_OK;
+  };
+  const sicp_status rc = body();
+  if (d_in) cudaFreeAsync(d_in, st);
+  if (d_out) cudaFreeAsync(d_out, st);
+  SICP_CHECK(rc);
+  std::memcpy(out7, h_out, 56);
+  if (lm_iterations) std::memcpy(lm_iterations, h_out + 7, sizeof(int));
+  return SICP_OK;
 }
 
 sicp_status sicp_filter_range(const void* xyz, size_t xyz_stride, size_t n, double range, int device, uint32_t* keep_idx_out, size_t* n_keep_out) {

@@ -32,6 +32,7 @@ namespace sicp {
 constexpr int kBatchConcurrent = 8;
 constexpr int kBatchLmVariant = 0;
 constexpr int kBatchLmGrid = 37;
+constexpr int kLoneCtlShare8 = 8, kBatchCtlShare8 = 8;  // sweep share of the LM controller block (eighths)
 constexpr int kGraphReuse = 1;  // 1: keep one graph exec per slot and update it in place for every registration
 
 static int env_int(const char* name, int dflt) {
@@ -50,6 +51,7 @@ static LMConfig make_cfg(int algo, const sicp_options& o) {
   c.mse_stop = algo == SICP_ALGO_SEMANTIC ? 1e-3 : 1e-5;    // semantic_icp.hpp:152 / gicp.hpp:154, em_icp.hpp:180
   c.outer_cap = algo == SICP_ALGO_SEMANTIC ? 35 : 50;
   c.variant = 0;
+  c.ctl_share8 = 8;
   return c;
 }
 
@@ -387,6 +389,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     jb.st = lone ? base : sl->st;
     jb.cfg = make_cfg(jb.algo, *jb.opts);
     jb.cfg.variant = variant;
+    jb.cfg.ctl_share8 = std::min(8, std::max(0, env_int("SICP_LM_CTL_SHARE", lone ? kLoneCtlShare8 : kBatchCtlShare8)));
     const int gmax = lm_max_grid(device, jb.algo, variant);
     jb.lm_grid = lone ? lm_grid_blocks(device) : std::min(gmax, std::max(1, env_int("SICP_LM_GRID", kBatchLmGrid)));
     jb.tm.on = jb.opts->profile != 0;

@@ -5,6 +5,7 @@
 // (impl/semantic_icp.hpp:27-166).
 #ifndef SICP_FACADE_SEMANTIC_ICP_H_
 #define SICP_FACADE_SEMANTIC_ICP_H_
+#include <iostream>
 #include "semantic_point_cloud.h"
 
 namespace semanticicp {
@@ -44,6 +45,32 @@ class SemanticIterativeClosestPoint {
   }
   Sophus::SE3d getFinalTransFormation() { return finalTransformation_; }  // semantic_icp.h:58 (sic)
   int getOuterIter() { return outer_iter; }                               // extension (GICP / EM have it)
+
+  // semantic_icp.h:78-81 (protected there and never called by align(): dead code in the reference; public here so that a
+  // caller who wants per-class pose fusion can reach them).  Both run on the device (sicp_iterative_mean, sicp_pose_fusion).
+  typedef std::vector<Eigen::Matrix<double, 6, 6>, Eigen::aligned_allocator<Eigen::Matrix<double, 6, 6>>> CovarianceVector;
+  Sophus::SE3d iterativeMean(std::vector<Sophus::SE3d> const& in, size_t maxIterations) {  // impl/semantic_icp.hpp:169-191
+    std::vector<double> p(7 * in.size());
+    for (std::size_t i = 0; i < in.size(); i++) detail::se3_to_pose7(in[i], &p[7 * i]);
+    double out[7];
+    int converged = 0;
+    detail::check(sicp_iterative_mean(in.size(), p.data(), (int)maxIterations, out, &converged), "iterativeMean");
+    if (!converged) std::cout << "Iterative Mean Failed";  // impl/semantic_icp.hpp:189
+    return detail::pose7_to_se3(out);
+  }
+  Sophus::SE3d poseFusion(std::vector<Sophus::SE3d> const& poses, CovarianceVector const& covs, Sophus::SE3d const& initTransform) {  // hpp:213-265
+    std::vector<double> p(7 * poses.size()), c(36 * covs.size());
+    for (std::size_t i = 0; i < poses.size(); i++) detail::se3_to_pose7(poses[i], &p[7 * i]);
+    for (std::size_t i = 0; i < covs.size(); i++)
+      for (int r = 0; r < 6; r++)
+        for (int q = 0; q < 6; q++) c[36 * i + 6 * r + q] = covs[i](r, q);
+    double init7[7], out[7];
+    detail::se3_to_pose7(initTransform, init7);
+    int iters = 0;
+    if (covs.size() != poses.size()) throw std::runtime_error("semanticicp (B200): poseFusion needs one covariance per pose");
+    detail::check(sicp_pose_fusion(poses.size(), p.data(), c.data(), init7, out, &iters), "poseFusion");
+    return detail::pose7_to_se3(out);
+  }
 
  protected:
   int outer_iter;

@@ -53,7 +53,7 @@ EXPORTS = [
     "sicp_cloud_get_normals", "sicp_cloud_get_label_distributions", "sicp_cloud_get_label_vectors", "sicp_cloud_get_self_neighbours",
     "sicp_cloud_get_classes", "sicp_knn", "sicp_knn_cloud", "sicp_correspondences", "sicp_evaluate", "sicp_register",
     "sicp_register_batch", "sicp_fused_labels", "sicp_cloud_transform_f32", "sicp_launch_count", "sicp_label_agreement",
-    "sicp_pose_errors", "sicp_filter_range",
+    "sicp_pose_errors", "sicp_filter_range", "sicp_iterative_mean", "sicp_pose_fusion",
 ]
 
 
@@ -371,3 +371,23 @@ class SemanticIterativeClosestPoint:
 
     def getFinalTransFormation(self):
         return self._res["pose"].copy()
+
+
+def iterative_mean(poses7, max_iterations=100):
+    """SemanticIterativeClosestPoint::iterativeMean (impl/semantic_icp.hpp:169-191): (mean pose7, converged)."""
+    p = np.ascontiguousarray(poses7, dtype=np.float64).reshape(-1, 7)
+    out = np.zeros(7)
+    conv = C.c_int(0)
+    _check(lib().sicp_iterative_mean(C.c_size_t(len(p)), _p(p), C.c_int(max_iterations), _p(out), C.byref(conv)))
+    return out, bool(conv.value)
+
+
+def pose_fusion(poses7, covs, init7):
+    """SemanticIterativeClosestPoint::poseFusion (impl/semantic_icp.hpp:193-265): (fused pose7, LM iterations)."""
+    p = np.ascontiguousarray(poses7, dtype=np.float64).reshape(-1, 7)
+    c = np.ascontiguousarray(covs, dtype=np.float64).reshape(-1, 36)
+    assert len(c) == len(p)
+    out = np.zeros(7)
+    it = C.c_int(0)
+    _check(lib().sicp_pose_fusion(C.c_size_t(len(p)), _p(p), _p(c), _p(np.ascontiguousarray(init7, dtype=np.float64)), _p(out), C.byref(it)))
+    return out, it.value

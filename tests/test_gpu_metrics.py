@@ -47,3 +47,31 @@ def test_filter_range_matches_oracle(sicp, oracle, pkg):
     edge = np.array([[3, 4, 0], [3, 4, 1e-3], [0, 0, 5], [np.nextafter(np.float32(5), np.float32(6)), 0, 0]], dtype=np.float32)
     assert list(sicp.filter_range(edge, 5.0)) == list(oracle.filter_range(edge, 5.0)) == [0, 2]   # `>` is strict: r == range stays
     assert len(sicp.filter_range(np.zeros((0, 3), dtype=np.float32), 40.0)) == 0
+
+
+@pytest.mark.gpu
+def test_iterative_mean_and_pose_fusion(sicp, oracle, pkg):
+    """§8(f) row 4 on the device (sicp_iterative_mean, sicp_pose_fusion) against the oracle's restatement of
+    impl/semantic_icp.hpp:169-265."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(8)
+    base = np.concatenate([Rotation.from_rotvec([0.1, -0.2, 0.05]).as_quat(), [1.0, 2.0, 0.5]])
+    for n, spread in ((1, 0.0), (9, 0.05), (40, 0.3)):  # 40 > one warp of residual blocks
+        poses = np.array([oracle.se3_plus(base, rng.normal(scale=spread, size=6)) for _ in range(n)])
+        got, ok = sicp.iterative_mean(poses, 100)
+        ref, rok = oracle.iterative_mean(poses, 100)
+        assert ok == rok and np.max(np.abs(got - ref)) < 1e-12
+        covs = np.array([np.diag(rng.uniform(0.5, 2, 6)) * 1e-4 + 1e-6 for _ in range(n)])
+        fused, it = sicp.pose_fusion(poses, covs, base)
+        rfused, rit = oracle.pose_fusion(poses, covs, base)
+        # both minimise the same objective with finite-difference Jacobians (rounded differently: FMA vs none) down to
+        # tolerances of 1e-14, where the cost is flat: the minimisers agree far inside the pose tolerance, not to the bit
+        rot, trans = pkg.synth.pose_error(fused, rfused)
+        assert rot < 1e-6 and trans < 1e-6, (rot, trans)
+        assert (it == 0) == (n == 1)
+    got, ok = sicp.iterative_mean(np.array([base, oracle.se3_plus(base, np.array([3.0, 0, 0, 0, 0, 2.5]))]), 1)
+    ref, rok = oracle.iterative_mean(np.array([base, oracle.se3_plus(base, np.array([3.0, 0, 0, 0, 0, 2.5]))]), 1)
+    assert ok == rok and np.max(np.abs(got - ref)) < 1e-12  # step limit reached: the last iterate is returned
+    with pytest.raises(sicp.SicpError):
+        sicp.iterative_mean(np.array([[0, 0, 0, 2.0, 0, 0, 0]]), 5)

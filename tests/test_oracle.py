@@ -298,3 +298,77 @@ def test_reference_runner_recipe_configures():
     with tempfile.TemporaryDirectory() as d:
         r = subprocess.run(["cmake", "-S", os.path.join(root, "oracle", "ref_build"), "-B", d], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def _random_poses(oracle, rng, n, spread):
+    from scipy.spatial.transform import Rotation
+
+    base = np.concatenate([Rotation.from_rotvec([0.1, -0.2, 0.05]).as_quat(), [1.0, 2.0, 0.5]])
+    return base, np.array([oracle.se3_plus(base, rng.normal(scale=spread)) for _ in range(n)])
+
+
+def test_iterative_mean_matches_numpy_transcription(oracle):
+    """SemanticIterativeClosestPoint::iterativeMean (impl/semantic_icp.hpp:169-191) against a scipy transcription that
+    shares no code with the oracle: same iterate after the same number of steps."""
+    from scipy.spatial.transform import Rotation
+
+    def to_M(p):
+        M = np.eye(4); M[:3, :3] = Rotation.from_quat(p[:4]).as_matrix(); M[:3, 3] = p[4:]
+        return M
+
+    def log6(M):  # Sophus order: upsilon, omega
+        om = Rotation.from_matrix(M[:3, :3]).as_rotvec()
+        th = np.linalg.norm(om); O = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0.0]])
+        V = np.eye(3) + 0.5 * O + O @ O / 6 if th < 1e-8 else np.eye(3) + (1 - np.cos(th)) / th**2 * O + (th - np.sin(th)) / th**3 * (O @ O)
+        return np.concatenate([np.linalg.solve(V, M[:3, 3]), om])
+
+    def exp6(d):
+        om = d[3:]; th = np.linalg.norm(om); O = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0.0]])
+        V = np.eye(3) + 0.5 * O + O @ O / 6 if th < 1e-8 else np.eye(3) + (1 - np.cos(th)) / th**2 * O + (th - np.sin(th)) / th**3 * (O @ O)
+        M = np.eye(4); M[:3, :3] = Rotation.from_rotvec(om).as_matrix(); M[:3, 3] = V @ d[:3]
+        return M
+
+    rng = np.random.default_rng(5)
+    for spread, n in ((np.array([0.05] * 3 + [0.02] * 3), 9), (np.array([0.5] * 3 + [0.3] * 3), 17)):
+        base, poses = _random_poses(oracle, rng, n, spread)
+        got, ok = oracle.iterative_mean(poses, 100)
+        avg = to_M(poses[0]); conv = False
+        for _ in range(100):
+            a = sum(log6(np.linalg.inv(avg) @ to_M(p)) for p in poses) / n
+            new = avg @ exp6(a)
+            done = np.sum(log6(np.linalg.inv(new) @ avg) ** 2) < 0.01
+            avg = new
+            if done:
+                conv = True
+                break
+        assert ok == conv
+        assert np.max(np.abs(to_M(got) - avg)) < 1e-12
+    one, ok = oracle.iterative_mean(poses[:1], 5)  # a single pose is its own mean
+    assert ok and np.max(np.abs(to_M(one) - to_M(poses[0]))) < 1e-14
+
+
+def test_pose_fusion_is_a_minimiser(oracle):
+    """SemanticIterativeClosestPoint::poseFusion (impl/semantic_icp.hpp:193-265): the fused pose must minimise
+    1/2 sum Huber_10((e^T W e)^2) — checked with an independent scipy minimisation restarted at the result."""
+    from scipy.optimize import minimize
+
+    rng = np.random.default_rng(6)
+    base, poses = _random_poses(oracle, rng, 9, np.array([0.05] * 3 + [0.02] * 3))
+    covs = np.array([np.diag(rng.uniform(0.5, 2, 6)) * 1e-4 for _ in range(9)])
+    covs[3] += 2e-5  # one dense covariance
+    fused, iters = oracle.pose_fusion(poses, covs, base)
+    assert 1 <= iters <= 50000
+    scale = np.mean([np.linalg.det(c) for c in covs]) ** (1 / 6)
+
+    def cost(delta):
+        T, c = oracle.se3_plus(fused, delta), 0.0
+        for p_, cv in zip(poses, covs):
+            e = oracle.se3_log(oracle.se3_mul(T, oracle.se3_inv(p_)))
+            s = (e @ (np.linalg.inv(cv) * scale) @ e) ** 2
+            c += 0.5 * (s if s <= 100 else 20 * np.sqrt(s) - 100)
+        return c
+
+    r = minimize(cost, np.zeros(6), method="Nelder-Mead", options=dict(xatol=1e-10, fatol=1e-16, maxiter=4000))
+    assert np.linalg.norm(r.x) < 1e-5 and cost(np.zeros(6)) - r.fun <= 1e-9 * max(r.fun, 1e-12)
+    single, it = oracle.pose_fusion(poses[:1], covs[:1], base)  # one pose: returned as is (hpp:223)
+    assert it == 0 and np.array_equal(single, poses[0])
