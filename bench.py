@@ -2,7 +2,7 @@
 """bench.py — scan-pair registrations/sec on KITTI-shaped semantic pairs (BASELINE.json configs[1]).
 
 One "step" = one batch of PAIRS independent EM-ICP registrations (120k-point labelled scan pairs, 20 classes,
-confusion-matrix EM) on one GPU: per pair, cloud construction (Hilbert sort + box tree) for both scans, k=20
+confusion-matrix EM) on one GPU: per pair, cloud construction (Morton sort + box tree) for both scans, k=20
 covariance / label-vector precompute, and every outer pass until the reference's stopping rule
 (reference span: exec/kitti_eval.cc:188-193).
 

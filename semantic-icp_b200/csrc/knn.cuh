@@ -36,14 +36,16 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
   return v;
 }
 #ifndef SICP_CURVE_HILBERT
-#define SICP_CURVE_HILBERT 1
+#define SICP_CURVE_HILBERT 0
 #endif
 // 30-bit space-filling-curve key (10 bits per axis) of (x,y,z) in the bounding cube described by bb (ordered ints, see
 // bbox_kernel).  The key only decides the ORDER of the points (which 32 of them share a leaf) and the home-leaf lookup;
-// search results do not depend on it.  Hilbert order (Skilling's transpose algorithm): consecutive keys are always
-// adjacent cells, so a run of 32 points never straddles one of the long jumps of the Z-order curve — on KITTI-shaped
-// scans the leaf boxes a query ball meets drop from 5.8 to 4.0 (k = 4) and the leaves a 32-query packet scans from
-// 13.7 to 9.4 (tools/sim_knn.py).  SICP_CURVE_HILBERT=0 builds the Z-order (Morton) variant for A/B runs.
+// search results do not depend on it.  Default: Z-order (Morton).  -DSICP_CURVE_HILBERT=1 builds the Hilbert variant
+// (Skilling's transpose algorithm: consecutive keys are always adjacent cells, so a run of 32 points never straddles one
+// of the long jumps of the Z-order curve).  Measured on KITTI-shaped scans (profiles/r2_knn_curve_ab.md): Hilbert order
+// cuts the leaves a 32-query packet scans from 12.2 to 9.2 (k = 4) and the instructions of the kernel by 12 %, but the
+// kernel's duration is set by its few heaviest packets (queries with no target point nearby in a dense region), which
+// get no lighter — a lone k = 4 search runs at 600 M queries/s against 688 M with Z-order, and batch throughput is equal.
 __device__ __forceinline__ uint32_t morton30(float x, float y, float z, const int* __restrict__ bb) {
   float lo[3], ext = 0.f;
 #pragma unroll
