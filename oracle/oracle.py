@@ -80,6 +80,13 @@ def knn(tgt, q, k, brute=False, threads=0):
     return idx, d2
 
 
+def knn_search_seconds():
+    """Seconds the search loop of the last knn() call took (the kd-tree build excluded)."""
+    f = lib().orc_knn_search_seconds
+    f.restype = C.c_double
+    return float(f())
+
+
 def transform_points(pose7, xyz):
     xyz = _f32(xyz)
     out = np.empty_like(xyz)

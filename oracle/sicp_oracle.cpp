@@ -932,9 +932,13 @@ int orc_num_threads() {
 #endif
 }
 
+static double g_knn_search_seconds = 0.0;  // the search loop of the last orc_knn call, tree build excluded (bench.py's q/s figure)
+double orc_knn_search_seconds() { return g_knn_search_seconds; }
+
 void orc_knn(const float* tgt, int nt, const float* q, int nq, int k, int32_t* idx, float* d2, int brute, int threads) {
   KdTree tree;
   if (!brute) tree.build(tgt, nt);
+  const double t_search = omp_get_wtime();
 #pragma omp parallel num_threads(threads > 0 ? threads : 1)
   {
     std::vector<Cand> buf(k);  // one scratch list per thread
@@ -949,6 +953,7 @@ void orc_knn(const float* tgt, int nt, const float* q, int nq, int k, int32_t* i
       }
     }
   }
+  g_knn_search_seconds = omp_get_wtime() - t_search;
 }
 
 void orc_transform_points(const double* pose7, const float* xyz, int n, float* out) {

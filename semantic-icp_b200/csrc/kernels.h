@@ -67,6 +67,12 @@ int lm_max_grid(int device, int algo, int variant);
 // "not converged" so that the graph runs another pass without the host
 sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const char* d_rec, RegCtl* d_ctl,
                       double* d_partials, int grid, cudaStream_t st, unsigned long long cond_handle = 0);
+// The inner solves of TWO registrations (same algorithm) in one cooperative launch whose sweeping blocks alternate between
+// them, so that each problem's control step overlaps the other's sweep (lm.cu: lm_pair_kernel).  cond_handle as above,
+// set to "some registration of the pair has not converged".
+sicp_status launch_lm_pair(const sicp_cloud* src0, const LMConfig& cfg0, const char* d_rec0, RegCtl* d_ctl0, double* d_partials0,
+                           const sicp_cloud* src1, const LMConfig& cfg1, const char* d_rec1, RegCtl* d_ctl1, double* d_partials1,
+                           int grid, cudaStream_t st, unsigned long long cond_handle);
 // Single evaluation (cost, g, H) at a given pose, for parity tests
 sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const char* d_rec,
                             const double* d_pose7, double* d_out28, double* d_partials, int grid, cudaStream_t st);

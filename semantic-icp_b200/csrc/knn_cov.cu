@@ -21,6 +21,23 @@ namespace sicp {
 constexpr int kWarpsPerBlock = SICP_WPB;
 constexpr int kThreads = kWarpsPerBlock * 32;
 
+// Which 32-query packet (leaf of the query cloud) a warp takes.  Expensive packets come in runs of neighbouring leaves
+// (a dense region whose queries have no target point nearby), and a block's warps share one SM: handing a block FOUR
+// CONSECUTIVE leaves puts a whole run on one SM, which then decides the kernel's duration (ncu: slowest SM busy 2.1x the
+// average).  Interleaving — warp w of block b takes leaf w * gridDim + b — spreads a run over neighbouring blocks / SMs,
+// but measured SLOWER (k = 4: 656 vs 687 M queries/s, k = 20: 209 vs 242): neighbouring packets share tree nodes and
+// leaves through L1, which is worth more than the balance.  Kept as a build option (-DSICP_INTERLEAVE=1), default off.
+#ifndef SICP_INTERLEAVE
+#define SICP_INTERLEAVE 0
+#endif
+__device__ __forceinline__ int packet_of_warp(int wib) {
+#if SICP_INTERLEAVE
+  return wib * (int)gridDim.x + (int)blockIdx.x;
+#else
+  return (int)blockIdx.x * kWarpsPerBlock + wib;
+#endif
+}
+
 // ------------------------------------------------------------------ Eigen::JacobiSVD<Matrix3d> restated (U's last column)
 struct Rot { double c, s; };
 __device__ __forceinline__ void make_jacobi(double x, double y, double z, Rot* r) {
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, co
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   __shared__ Segment s_seg[kWarpsPerBlock];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int leaf = blockIdx.x * kWarpsPerBlock + wib;
+  const int leaf = packet_of_warp(wib);
   if (leaf * kLeaf >= cv.nslots) return;
   const int sid = cv.seg_of_leaf[leaf];
   if (lane == 0) s_seg[wib] = cv.seg[sid];
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(kThreads) cross_knn_kernel(CloudView sv, Cloud
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   __shared__ Segment s_seg[kWarpsPerBlock];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int leaf = blockIdx.x * kWarpsPerBlock + wib;
+  const int leaf = packet_of_warp(wib);
   if (leaf * kLeaf >= sv.nslots) return;
   const int slot = leaf * kLeaf + lane;
   const int tsid = tseg_of_sseg ? tseg_of_sseg[sv.seg_of_leaf[leaf]] : 0;

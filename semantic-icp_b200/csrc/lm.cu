@@ -559,10 +559,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 // Per-warp double buffer of group blocks.  `uses` counts the blocks consumed so far over the whole launch: use u lives in
 // buffer u & 1 and completes phase (u >> 1) & 1 of that buffer's barrier.
 struct GroupPipe {
-  char* buf;        // 2 * group_bytes of shared memory owned by this warp
-  unsigned bar;     // shared address of its two 8-byte barriers
+  char* buf;               // 2 * group_bytes of shared memory owned by this warp
+  unsigned bar;            // shared address of its two 8-byte barriers
   unsigned uses;
-  bool primed;      // the copy for use `uses` is already in flight (issued at the end of the previous sweep)
+  const char* primed_src;  // != null: the copy for use `uses` is already in flight from this address (issued as the previous sweep ended)
 };
 
 // Residual sweep at the pose (P.R, P.t): one thread owns one source slot and its KC records.
@@ -579,26 +579,40 @@ struct GroupPipe {
 // current one is evaluated out of shared memory, so the FP64 pipe never waits on an L2 round trip; the first block of
 // the next sweep is fetched as this sweep ends (the records do not change during a solve) and is already waiting when
 // the controller publishes the next pose.
+// Work split of a sweep: a block owns a contiguous range [g0, g1) of the groups and deals them to its warps round-robin,
+// so the four schedulers of an SM carry the same number of groups (+-1).  `worker` of `nworkers` equal shares; in the
+// single-problem kernel the controller block (block 0) takes ctl_share8 / 8 of a normal share (0 = it does not sweep).
+__device__ __forceinline__ void group_range(int ngroups, long long u0, long long u1, long long units, int* g0, int* g1) {
+  *g0 = (int)(((long long)ngroups * u0) / units);
+  *g1 = (int)(((long long)ngroups * u1) / units);
+}
+// address of the first group block this warp reads in a sweep over [g0, g1) of `rec` (null: none)
+template <int KC>
+__device__ __forceinline__ const char* first_block(const char* rec, int g0, int g1) {
+  const int gfirst = g0 + (threadIdx.x >> 5);
+  return gfirst < g1 ? rec + (size_t)gfirst * Rec::group_bytes(KC) : nullptr;
+}
+// next_src: first block of the sweep this warp will run NEXT (same problem, or the other one of a pair): prefetched as this
+// sweep ends.
 template <int ALGO, int KC, int THREADS>
-__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc, GroupPipe& pp) {
+__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc, GroupPipe& pp, int g0, int g1, const char* next_src) {
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
   constexpr unsigned GB = Rec::group_bytes(KC);
   constexpr int W = THREADS / 32;
-  // Work split: a block owns a contiguous range of groups and deals them to its warps round-robin, so the four
-  // schedulers of an SM carry the same number of groups (+-1).
-  const int ngroups = a.sv.nslots >> 5;
-  // The controller block (block 0) takes ctl_share / 8 of a normal share (0 = it does not sweep): it then never is the
-  // late arrival it would itself be waiting for, which shortens the serial reduce-decide-publish section between sweeps.
-  const long long units = 8ll * (gridDim.x - 1) + a.cfg.ctl_share8;  // eighths of a share
-  const long long u0 = blockIdx.x == 0 ? 0 : a.cfg.ctl_share8 + 8ll * (blockIdx.x - 1);
-  const long long u1 = blockIdx.x == 0 ? a.cfg.ctl_share8 : u0 + 8;
-  const int g0 = (int)(((long long)ngroups * u0) / units), g1 = (int)(((long long)ngroups * u1) / units);
   const int lane = threadIdx.x & 31;
   const int gfirst = g0 + (threadIdx.x >> 5);
-  if (gfirst >= g1) return;
   const char* rec = a.rec;
-  if (!pp.primed && lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), rec + (size_t)gfirst * GB, GB, pp.bar + 8 * (pp.uses & 1));
+  const char* want = gfirst < g1 ? rec + (size_t)gfirst * GB : nullptr;
+  if (pp.primed_src != want) {
+    if (pp.primed_src) {  // a block of another sweep is in flight (the other problem of a pair finished meanwhile): let it land, drop it
+      mbar_wait(pp.bar + 8 * (pp.uses & 1), (pp.uses >> 1) & 1);
+      pp.uses++;
+      __syncwarp();
+    }
+    if (want && lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), want, GB, pp.bar + 8 * (pp.uses & 1));
+  }
+  pp.primed_src = nullptr;
   for (int g = gfirst; g < g1; g += W) {
     __syncwarp();  // every lane is done with the buffer the next copy lands in (it was read one iteration ago)
     if (lane == 0 && g + W < g1) bulk_load(smem_u32(pp.buf + ((pp.uses + 1) & 1) * GB), rec + (size_t)(g + W) * GB, GB, pp.bar + 8 * ((pp.uses + 1) & 1));
@@ -660,14 +674,14 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
     }
   }
   __syncwarp();
-  if (lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), rec + (size_t)gfirst * GB, GB, pp.bar + 8 * (pp.uses & 1));
-  pp.primed = true;
+  if (next_src && lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), next_src, GB, pp.bar + 8 * (pp.uses & 1));
+  pp.primed_src = next_src;
 }
 // a block may only exit (and hand its shared memory back) once no bulk copy is in flight into it
 template <int KC, int THREADS>
 __device__ __forceinline__ void pipe_drain(GroupPipe& pp) {
-  if (pp.primed) mbar_wait(pp.bar + 8 * (pp.uses & 1), (pp.uses >> 1) & 1);
-  pp.primed = false;
+  if (pp.primed_src) mbar_wait(pp.bar + 8 * (pp.uses & 1), (pp.uses >> 1) & 1);
+  pp.primed_src = nullptr;
 }
 
 // Block reduction of the 28 per-thread sums through shared memory (fixed order => deterministic): every thread
@@ -698,7 +712,7 @@ __device__ __forceinline__ void block_reduce(const double* acc, double* s_acc, d
 // Fixed-order sum of the block partials by the controller block: warp `sub` sums blocks sub, sub+8, ... with
 // independent loads, then the 8 warp sums are added in order.  Result in s_tot[0..27].
 template <int THREADS>
-__device__ __forceinline__ void reduce_partials(const double* part, double (*s_red)[kAcc], double* s_tot) {
+__device__ __forceinline__ void reduce_partials(const double* part, double (*s_red)[kAcc], double* s_tot, int b0 = 0) {
   constexpr int kLmWarps = THREADS / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0;
@@ -707,7 +721,7 @@ __device__ __forceinline__ void reduce_partials(const double* part, double (*s_r
     double v[kMaxPerWarp];
 #pragma unroll
     for (int k = 0; k < kMaxPerWarp; k++) {
-      const int bI = warp + kLmWarps * k;
+      const int bI = b0 + warp + kLmWarps * k;
       v[k] = bI < (int)gridDim.x ? __ldcg(&part[(size_t)bI * kAcc + lane]) : 0.0;
     }
 #pragma unroll
@@ -747,6 +761,33 @@ __device__ __forceinline__ void rotate_totals(const double* s_tot, const double*
   }
 }
 
+// Outer-loop bookkeeping when an inner solve has terminated (one thread): mse = |log(cur^-1 est)|^2 (impl/gicp.hpp:153),
+// the stopping rule, the pass trace.  Returns `converged`.
+template <int ALGO>
+__device__ __forceinline__ bool finish_pass(RegCtl* c, const LMState& S, const LMConfig& cfg) {
+  double lg[6];
+  pose_log(pose_mul(pose_inv(pose_from7(c->pose)), pose_from7(S.x)), lg);
+  double mse = 0;
+  for (int i = 0; i < 6; i++) mse += lg[i] * lg[i];
+  const int before = c->outer;
+  bool conv;
+  if (ALGO == SICP_ALGO_SEMANTIC) conv = (mse < cfg.mse_stop) || (before + 1 > cfg.outer_cap);  // count++ first (semantic_icp.hpp:47)
+  else conv = (mse < cfg.mse_stop) || (before > cfg.outer_cap);
+  if (before < 64) { for (int i = 0; i < 7; i++) c->pass_pose[before][i] = S.x[i]; c->pass_lm_iters[before] = S.iter; }
+  for (int i = 0; i < 7; i++) c->pose[i] = S.x[i];
+  c->outer = before + 1;
+  c->lm_iters_total += S.iter;
+  c->lm_evals_total += S.evals;
+  c->term_last = S.term;
+  c->n_corr_last = c->n_corr_pass;
+  c->n_corr_pass = 0;
+  c->final_cost = S.cost;
+  c->last_mse = mse;
+  if (conv && !(mse < cfg.mse_stop)) c->flags |= 1;
+  c->converged = conv ? 1 : 0;
+  return conv;
+}
+
 // One inner solve (+ the outer-loop test) per launch.  Block 0 is the CONTROLLER: after every sweep the other blocks
 // signal arrival on a counter and wait on a generation flag; block 0 waits for the counter, sums the block partials,
 // runs the LM control step on solver state that stays in ITS shared memory for the whole solve, and publishes the next
@@ -777,12 +818,19 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
   pp.buf = s_pipe + (size_t)(threadIdx.x >> 5) * 2 * Rec::group_bytes(KC);
   pp.bar = smem_u32(&s_bar[2 * (threadIdx.x >> 5)]);
   pp.uses = 0;
-  pp.primed = false;
+  pp.primed_src = nullptr;
   if ((threadIdx.x & 31) == 0) {
     mbar_init(pp.bar, 1);
     mbar_init(pp.bar + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  int g0, g1;
+  {
+    const long long units = 8ll * (gridDim.x - 1) + a.cfg.ctl_share8;  // eighths of a share
+    const long long u0 = blockIdx.x == 0 ? 0 : a.cfg.ctl_share8 + 8ll * (blockIdx.x - 1);
+    group_range(a.sv.nslots >> 5, u0, blockIdx.x == 0 ? a.cfg.ctl_share8 : u0 + 8, units, &g0, &g1);
+  }
+  const char* my_first = first_block<KC>(a.rec, g0, g1);
   __syncthreads();
   if (s_x[7] != 0.0) {  // registration already converged: passes enqueued ahead of the host return at once
     if (a.cond && controller && threadIdx.x == 0) cudaGraphSetConditional(a.cond, 0u);  // never leave a graph loop running
@@ -799,7 +847,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
     }
     __syncthreads();
     double acc[kAcc];
-    sweep_acc<ALGO, KC, THREADS>(a, s_RT, acc, pp);
+    sweep_acc<ALGO, KC, THREADS>(a, s_RT, acc, pp, g0, g1, eval_only ? nullptr : my_first);
     block_reduce<THREADS>(acc, s_acc, a.partials);
     gen++;
     __syncthreads();  // the block's partial sums are written; thread 0's gpu-scope fence below is cumulative over them
@@ -850,28 +898,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
       if (threadIdx.x == 0) {
         t_lm += clock64() - t1;
         if (S.done) {
-          // outer-loop bookkeeping: mse = |log(cur^-1 est)|^2 (impl/gicp.hpp:153), stop rule, pass trace
-          RegCtl* c = a.ctl;
-          double lg[6];
-          pose_log(pose_mul(pose_inv(pose_from7(c->pose)), pose_from7(S.x)), lg);
-          double mse = 0;
-          for (int i = 0; i < 6; i++) mse += lg[i] * lg[i];
-          const int before = c->outer;
-          bool conv;
-          if (ALGO == SICP_ALGO_SEMANTIC) conv = (mse < a.cfg.mse_stop) || (before + 1 > a.cfg.outer_cap);  // count++ first (semantic_icp.hpp:47)
-          else conv = (mse < a.cfg.mse_stop) || (before > a.cfg.outer_cap);
-          if (before < 64) { for (int i = 0; i < 7; i++) c->pass_pose[before][i] = S.x[i]; c->pass_lm_iters[before] = S.iter; }
-          for (int i = 0; i < 7; i++) c->pose[i] = S.x[i];
-          c->outer = before + 1;
-          c->lm_iters_total += S.iter;
-          c->lm_evals_total += S.evals;
-          c->term_last = S.term;
-          c->n_corr_last = c->n_corr_pass;
-          c->n_corr_pass = 0;
-          c->final_cost = S.cost;
-          c->last_mse = mse;
-          if (conv && !(mse < a.cfg.mse_stop)) c->flags |= 1;
-          c->converged = conv ? 1 : 0;
+          const bool conv = finish_pass<ALGO>(a.ctl, S, a.cfg);
           if (a.cond) cudaGraphSetConditional(a.cond, conv ? 0u : 1u);  // graph WHILE body: run another pass?
         }
         for (int i = 0; i < 7; i++) { s_x[i] = S.cand[i]; sy->bcast[i] = S.cand[i]; }
@@ -897,6 +924,153 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
     a.ctl->dbg_cycles[4] += t_red;
     a.ctl->dbg_cycles[6] += t_lm;
   }
+}
+
+// ------------------------------------------------------------------ K4 + K5 for TWO registrations at once
+// The single-problem kernel idles every sweeping block while block 0 reduces, decides and publishes (ncu on a 37-block
+// solve: 27 % of the stall samples sit in that gap).  Here the sweeping blocks ALTERNATE between the solves of two
+// independent registrations: while the controller of problem A (block 0, which does not sweep) works on A's totals,
+// everyone else sweeps problem B, and vice versa (controller of B: block 1).  As long as a control step is shorter than a
+// sweep, the gap disappears from the critical path.  Each problem keeps its own LMSync / partials / RegCtl, its own
+// fixed-order reduction and its own LM state, so its results are what a solve on (gridDim - 2) blocks of the
+// single-problem kernel gives.  The launch ends when both solves have terminated; whichever controller finishes last sets
+// the graph's WHILE condition to "some registration of the pair has not converged".
+struct LMPairArgs { LMArgs p[2]; };
+
+template <int ALGO, int KC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) lm_pair_kernel(LMPairArgs pa) {
+  extern __shared__ __align__(128) unsigned char s_dyn[];
+  double* s_acc = reinterpret_cast<double*>(s_dyn);
+  char* s_pipe = reinterpret_cast<char*>(s_dyn) + sizeof(double) * kAcc * THREADS;
+  __shared__ __align__(8) unsigned long long s_bar[2 * (THREADS / 32)];
+  __shared__ LMState S;
+  __shared__ double s_red[THREADS / 32][kAcc];
+  __shared__ double s_tot[kAcc];
+  __shared__ double s_rot[kAcc];
+  __shared__ double s_x[2][8];  // per problem: pose to evaluate [7] + done flag
+  __shared__ double s_RT[12];
+  __shared__ double s_L[36];
+  const int nsweep = (int)gridDim.x - 2;
+  if (threadIdx.x < 16) {
+    const int p = threadIdx.x >> 3, i = threadIdx.x & 7;
+    s_x[p][i] = i < 7 ? pa.p[p].ctl->pose[i] : (double)pa.p[p].ctl->converged;
+  }
+  GroupPipe pp;
+  pp.buf = s_pipe + (size_t)(threadIdx.x >> 5) * 2 * Rec::group_bytes(KC);
+  pp.bar = smem_u32(&s_bar[2 * (threadIdx.x >> 5)]);
+  pp.uses = 0;
+  pp.primed_src = nullptr;
+  if ((threadIdx.x & 31) == 0) {
+    mbar_init(pp.bar, 1);
+    mbar_init(pp.bar + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (blockIdx.x < 2) {
+    // ---------------- controller of problem p
+    const int p = blockIdx.x;
+    const LMArgs& a = pa.p[p];
+    LMSync* sy = a.sync;
+    if (s_x[p][7] == 0.0) {
+      unsigned gen = ld_acquire(&sy->flag);
+      if (threadIdx.x == 0) S.started = 0;
+      __syncthreads();
+      for (;;) {
+        if (threadIdx.x == 0) {
+          quat_to_R(s_x[p], s_RT);
+          while (ld_acquire(&sy->count) != (unsigned)nsweep) { }
+        }
+        gen++;
+        __syncthreads();
+        reduce_partials<THREADS>(a.partials, s_red, s_tot, 2);
+        rotate_totals(s_tot, s_RT, s_rot);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+          const int was_started = S.started;
+          __syncwarp();
+          if (threadIdx.x == 0 && !was_started) {
+            double* ss = reinterpret_cast<double*>(&S);
+            for (int i = 0; i < (int)(sizeof(LMState) / sizeof(double)); i++) ss[i] = 0.0;
+            for (int i = 0; i < 7; i++) S.x[i] = s_x[p][i];
+          }
+          __syncwarp();
+          lm_control_warp(S, s_rot, a.cfg.max_iter, s_L, threadIdx.x);
+        }
+        if (threadIdx.x == 0) {
+          if (S.done) finish_pass<ALGO>(a.ctl, S, a.cfg);
+          for (int i = 0; i < 7; i++) { s_x[p][i] = S.cand[i]; sy->bcast[i] = S.cand[i]; }
+          s_x[p][7] = S.done ? 1.0 : 0.0;
+          sy->bcast[7] = s_x[p][7];
+          sy->count = 0;
+          st_release(&sy->flag, gen);
+        }
+        __syncthreads();
+        if (s_x[p][7] != 0.0) break;
+      }
+    }
+    // whichever controller finishes last decides whether the pair needs another pass
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned* pair_done = &pa.p[0].sync->pad[0];
+      const unsigned old = atomicAdd(pair_done, 1u);
+      if (old == 1u) {
+        __threadfence();
+        const int c0 = *((volatile int*)&pa.p[0].ctl->converged), c1 = *((volatile int*)&pa.p[1].ctl->converged);
+        *pair_done = 0u;
+        if (pa.p[0].cond) cudaGraphSetConditional(pa.p[0].cond, (c0 && c1) ? 0u : 1u);
+      }
+    }
+    return;
+  }
+
+  // ---------------- sweeping block: alternate between the two problems
+  int g0[2], g1[2];
+  const char* first[2];
+  unsigned gen[2];
+  bool done[2], started[2] = {false, false};
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+    group_range(pa.p[p].sv.nslots >> 5, (long long)blockIdx.x - 2, (long long)blockIdx.x - 1, nsweep, &g0[p], &g1[p]);
+    first[p] = first_block<KC>(pa.p[p].rec, g0[p], g1[p]);
+    done[p] = s_x[p][7] != 0.0;
+    gen[p] = ld_acquire(&pa.p[p].sync->flag);
+  }
+  for (;;) {
+    if (done[0] && done[1]) break;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+      if (done[p]) continue;
+      const LMArgs& a = pa.p[p];
+      LMSync* sy = a.sync;
+      if (started[p]) {  // the pose of the next evaluation of problem p (published while the other problem was swept)
+        if (threadIdx.x < 8) {
+          while ((int)(ld_acquire(&sy->flag) - gen[p]) < 0) { }
+          s_x[p][threadIdx.x] = __ldcg(&sy->bcast[threadIdx.x]);
+        }
+        __syncthreads();
+        if (s_x[p][7] != 0.0) { done[p] = true; continue; }
+      }
+      started[p] = true;
+      if (threadIdx.x == 0) {
+        quat_to_R(s_x[p], s_RT);
+        s_RT[9] = s_x[p][4]; s_RT[10] = s_x[p][5]; s_RT[11] = s_x[p][6];
+      }
+      __syncthreads();
+      double acc[kAcc];
+      // what this warp reads next: the other problem's first block while that problem is still running, else this one's again
+      const char* next_src = !done[1 - p] ? first[1 - p] : first[p];
+      sweep_acc<ALGO, KC, THREADS>(a, s_RT, acc, pp, g0[p], g1[p], next_src);
+      block_reduce<THREADS>(acc, s_acc, a.partials);
+      gen[p]++;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&sy->count, 1u);
+      }
+    }
+  }
+  pipe_drain<KC, THREADS>(pp);
 }
 
 // ------------------------------------------------------------------ fused labels (impl/em_icp.hpp:202-268)
@@ -1135,6 +1309,37 @@ sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const char* d_
               (cudaGraphConditionalHandle)cond_handle};
   static_assert(sizeof(LMSync) <= sizeof(double) * kLmSyncDoubles, "LMSync must fit in front of the partials");
   return launch_lm_args(args, grid, st);
+}
+
+// Two registrations' inner solves in one launch (lm_pair_kernel).  Both problems must use the same algorithm.
+static void* lm_pair_entry(int algo) {
+  switch (algo) {
+    case SICP_ALGO_GICP: return (void*)lm_pair_kernel<SICP_ALGO_GICP, 1, 256>;
+    case SICP_ALGO_SEMANTIC: return (void*)lm_pair_kernel<SICP_ALGO_SEMANTIC, 1, 256>;
+    default: return (void*)lm_pair_kernel<SICP_ALGO_EM, 4, 256>;
+  }
+}
+sicp_status launch_lm_pair(const sicp_cloud* src0, const LMConfig& cfg0, const char* d_rec0, RegCtl* d_ctl0, double* d_partials0,
+                           const sicp_cloud* src1, const LMConfig& cfg1, const char* d_rec1, RegCtl* d_ctl1, double* d_partials1,
+                           int grid, cudaStream_t st, unsigned long long cond_handle) {
+  SICP_REQUIRE(cfg0.algo == cfg1.algo, "a pair solve needs two registrations of the same algorithm");
+  LMPairArgs pa;
+  pa.p[0] = LMArgs{src0->view(), cfg0, d_rec0, d_ctl0, reinterpret_cast<double*>(d_partials0) + kLmSyncDoubles, reinterpret_cast<LMSync*>(d_partials0), nullptr, nullptr,
+                   (cudaGraphConditionalHandle)cond_handle};
+  pa.p[1] = LMArgs{src1->view(), cfg1, d_rec1, d_ctl1, reinterpret_cast<double*>(d_partials1) + kLmSyncDoubles, reinterpret_cast<LMSync*>(d_partials1), nullptr, nullptr, 0};
+  int dev = 0, sms = 148;
+  SICP_CUDA(cudaGetDevice(&dev));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  void* fn = lm_pair_entry(cfg0.algo);
+  const size_t smem = lm_smem(cfg0.algo, 0);
+  static bool attr_set[3] = {false, false, false};
+  const int ai = cfg0.algo == SICP_ALGO_GICP ? 0 : cfg0.algo == SICP_ALGO_SEMANTIC ? 1 : 2;
+  if (!attr_set[ai]) { SICP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set[ai] = true; }
+  grid = std::max(3, std::min(grid, std::min(sms, kLmMaxGrid)));  // two controller blocks + at least one sweeping block
+  void* params[] = {&pa};
+  SICP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), params, smem, st));
+  count_launches(1);
+  return SICP_OK;
 }
 
 sicp_status launch_evaluate(const sicp_cloud* src, const LMConfig& cfg, const char* d_rec,

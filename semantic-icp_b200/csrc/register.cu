@@ -33,6 +33,12 @@ constexpr int kBatchConcurrent = 8;
 constexpr int kBatchLmVariant = 0;
 constexpr int kBatchLmGrid = 37;
 constexpr int kLoneCtlShare8 = 8, kBatchCtlShare8 = 8;  // sweep share of the LM controller block (eighths)
+// Pairing (SICP_PAIR=1): registrations of a batch run in pairs that share one LM launch per pass, whose blocks alternate
+// between the two solves so that each control step overlaps the other's sweep.  Measured on one B200 (tools/sweep.py, 16
+// KITTI pairs): 388 registrations/s paired vs 390 unpaired, pass loop alone 20.8 vs 20.3 ms — in a batch the control gaps
+// are already filled by the other registrations in flight, and the lockstep costs what the overlap gains.  Off by default.
+constexpr int kPairDefault = 0;
+constexpr int kBatchLmPairGrid = 74;  // CTAs of a paired solve in a batch (2 controllers + 72 sweeping blocks)
 constexpr int kGraphReuse = 1;  // 1: keep one graph exec per slot and update it in place for every registration
 
 static int env_int(const char* name, int dflt) {
@@ -142,7 +148,8 @@ struct Slot {
   RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
   RegCtl* h_ctl = nullptr;        // pinned
   int* h_map = nullptr;           // pinned, kMaxSegMap ints (class map staging)
-  cudaGraphExec_t exec = nullptr;
+  cudaGraphExec_t exec = nullptr;       // WHILE { kNN, E-step, LM } of one registration
+  cudaGraphExec_t exec_pair = nullptr;  // ... of a pair of registrations (two kNN + E-step chains, one paired LM launch)
   SlotNote note{nullptr, 0};
   static constexpr int kMaxSegMap = 256;
 
@@ -180,6 +187,7 @@ struct Slot {
     if (device < 0) return;
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return; }  // context already gone (process exit)
     if (exec) cudaGraphExecDestroy(exec);
+    if (exec_pair) cudaGraphExecDestroy(exec_pair);
     free_records();
     cudaFree(d_ctl); cudaFree(d_partials); cudaFree(d_map);
     if (h_ctl) cudaFreeHost(h_ctl);
@@ -235,6 +243,14 @@ struct Job {
   sicp_result* out; Slot* sl = nullptr; cudaStream_t st = nullptr; int lm_grid = 0;
   int enqueued = 0; bool finished = false; bool graphed = false; int d2h = 0;
   cudaEvent_t trace_ref = nullptr; int trace_id = 0;
+  // Pairing (batches): the LEADER of a pair drives both registrations on its stream — their passes run in lockstep and
+  // their inner solves share one launch whose blocks alternate between the two problems (lm.cu: lm_pair_kernel).  The
+  // partner only contributes its slot's workspace and its own control block.
+  Job* partner = nullptr;
+  bool follower = false;
+  int pair_grid = 0;
+  Slot* idle_partner = nullptr;  // odd job of a paired batch: runs the paired kernel against an already-converged dummy, so that
+                                 // every registration of the batch is summed in the same block order (bit-identical results)
 
   // class map of SemanticICP (semantic_icp.hpp:50-51) through the slot's pinned staging: no host synchronisation
   sicp_status stage_class_map() {
@@ -258,8 +274,8 @@ struct Job {
     return SICP_OK;
   }
   const int* class_map() const { return cfg.algo == SICP_ALGO_SEMANTIC ? sl->d_map : nullptr; }
-  // the three kernels of one outer pass on stream `s` (the slot's stream, or the capture stream of the graph build)
-  sicp_status enqueue_pass(cudaStream_t s, unsigned long long cond) {
+  // correspondences + E-step of one outer pass on stream `s`
+  sicp_status enqueue_corr(cudaStream_t s) {
     const int* stop = &sl->d_ctl->converged;
     tm.begin(SICP_STAGE_KNN, s);
     SICP_CHECK(launch_cross_knn(src, tgt, sl->d_ctl->pose, stop, class_map(), cfg.kc, sl->d_corr, sl->d_d2, s));
@@ -267,6 +283,21 @@ struct Job {
     tm.begin(SICP_STAGE_ESTEP, s);
     SICP_CHECK(launch_estep(src, tgt, cfg, opts->gate_d2, sl->d_ctl->pose, stop, sl->d_corr, sl->d_d2, sl->d_rec, sl->d_ctl, s));
     tm.end(s);
+    return SICP_OK;
+  }
+  // the kernels of one outer pass on stream `s` (the slot's stream, or the capture stream of the graph build)
+  sicp_status enqueue_pass(cudaStream_t s, unsigned long long cond) {
+    SICP_CHECK(enqueue_corr(s));
+    if (partner) {
+      SICP_CHECK(partner->enqueue_corr(s));
+      SICP_CHECK(launch_lm_pair(src, cfg, sl->d_rec, sl->d_ctl, sl->d_partials, partner->src, partner->cfg, partner->sl->d_rec, partner->sl->d_ctl,
+                                partner->sl->d_partials, pair_grid, s, cond));
+      return SICP_OK;
+    }
+    if (idle_partner) {
+      SICP_CHECK(launch_lm_pair(src, cfg, sl->d_rec, sl->d_ctl, sl->d_partials, src, cfg, sl->d_rec, idle_partner->d_ctl, idle_partner->d_partials, pair_grid, s, cond));
+      return SICP_OK;
+    }
     tm.begin(SICP_STAGE_LM, s);
     SICP_CHECK(launch_lm(src, cfg, sl->d_rec, sl->d_ctl, sl->d_partials, lm_grid, s, cond));
     tm.end(s);
@@ -293,15 +324,16 @@ struct Job {
       SICP_CHECK(rc);
       SICP_CUDA(e);
       const int reuse = env_int("SICP_GRAPH_REUSE", kGraphReuse);
-      if (sl->exec && reuse) {  // same topology as the previous registration of this slot: update the kernel parameters in place
+      cudaGraphExec_t& ex = partner ? sl->exec_pair : sl->exec;
+      if (ex && reuse) {  // same topology as the previous registration of this slot: update the kernel parameters in place
         cudaGraphExecUpdateResultInfo info;
-        if (cudaGraphExecUpdate(sl->exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(sl->exec); sl->exec = nullptr; }
-      } else if (sl->exec) {
-        cudaGraphExecDestroy(sl->exec);  // the previous registration of this slot has completed (its readback was consumed)
-        sl->exec = nullptr;
+        if (cudaGraphExecUpdate(ex, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(ex); ex = nullptr; }
+      } else if (ex) {
+        cudaGraphExecDestroy(ex);  // the previous registration of this slot has completed (its readback was consumed)
+        ex = nullptr;
       }
-      if (!sl->exec) SICP_CUDA(cudaGraphInstantiate(&sl->exec, g, 0));
-      SICP_CUDA(cudaGraphLaunch(sl->exec, st));
+      if (!ex) SICP_CUDA(cudaGraphInstantiate(&ex, g, 0));
+      SICP_CUDA(cudaGraphLaunch(ex, st));
       return SICP_OK;
     };
     const sicp_status rc = build();
@@ -326,11 +358,18 @@ struct Job {
     }
     SICP_CUDA(cudaMemcpyAsync(sl->h_ctl, sl->d_ctl, sizeof(RegCtl), cudaMemcpyDeviceToHost, st));
     d2h += (int)sizeof(RegCtl);
+    if (partner) {
+      SICP_CUDA(cudaMemcpyAsync(partner->sl->h_ctl, partner->sl->d_ctl, sizeof(RegCtl), cudaMemcpyDeviceToHost, st));
+      partner->d2h += (int)sizeof(RegCtl);
+      partner->graphed = graphed;
+    }
     if (sl->note.c) SICP_CUDA(cudaLaunchHostFunc(st, note_done, &sl->note));
     return SICP_OK;
   }
   // after the readback has landed: true when the registration is complete
-  bool complete() const { return sl->h_ctl->converged != 0 || enqueued >= cfg.outer_cap + 2; }
+  bool complete() const {
+    return (sl->h_ctl->converged != 0 && (!partner || partner->sl->h_ctl->converged != 0)) || enqueued >= cfg.outer_cap + 2;
+  }
   void finish() {
     const RegCtl& c = *sl->h_ctl;
     std::memcpy(out->pose7, c.pose, 56);
@@ -343,7 +382,8 @@ struct Job {
     for (int i = 0; i < 3; i++) out->lm_cycles[i] = (double)c.dbg_cycles[i];
     for (int i = 0; i < 3; i++) out->lm_cycles[3 + i] = (double)c.dbg_cycles[4 + i];
     out->gpu_launches = c.outer * 3;  // kernels that did work (the graph loop launches exactly these; the pass-by-pass path may add early-exit launches)
-    if (graphed) count_launches(c.outer * 3 - 3);  // the capture counted one pass
+    if (graphed && partner) count_launches(5 * std::max(c.outer, partner->sl->h_ctl->outer) - 5);  // a pair's pass: 2 kNN + 2 E-step + 1 paired LM
+    else if (graphed && !follower) count_launches(c.outer * 3 - 3);  // the capture counted one pass
     tm.collect(out, trace_ref, trace_id);
     finished = true;
   }
@@ -361,7 +401,11 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   for (const Job& jb : jobs) nc_max = std::max(nc_max, (size_t)jb.src->nslots * (jb.algo == SICP_ALGO_EM ? 4 : 1));
   Completion done_q;
   cudaEvent_t fork = nullptr;
-  for (int s = 0; s < S; s++) {
+  // Pairing: two registrations share a leader slot's stream and graph and one paired LM launch per pass (see Job::partner).
+  bool pairing = !lone && nj >= 2 && env_int("SICP_PAIR", kPairDefault) != 0;
+  for (const Job& jb : jobs) pairing = pairing && jb.algo == jobs[0].algo && jb.opts->profile == 0;
+  const int NS = pairing ? std::max(1, S / 2) : S;  // leader slots in flight; a pair also uses the workspace of slot NS + s
+  for (int s = 0; s < (pairing ? 2 * NS : NS); s++) {
     Slot* sl = t_pool.get(s);
     SICP_CHECK(sl->ensure(device, nc_max));
     sl->note = SlotNote{&done_q, s};
@@ -378,15 +422,13 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   // the other registrations in flight share those SMs.
   const int variant = lone ? 0 : std::min(std::max(env_int("SICP_LM_VARIANT", kBatchLmVariant), 0), kLmVariants - 1);
   sicp_status rc = SICP_OK;
-  std::vector<int> slot_job(S, -1);
+  std::vector<int> slot_job(NS, -1);
   int next = 0, live = 0;
-  auto launch = [&](int slot) -> sicp_status {
-    const int j = next++;
-    slot_job[slot] = j;
+  // everything a registration needs before its passes, on stream `st` with the workspace of `sl`
+  auto prepare = [&](int j, Slot* sl, cudaStream_t st) -> sicp_status {
     Job& jb = jobs[j];
-    Slot* sl = t_pool.get(slot);
     jb.sl = sl;
-    jb.st = lone ? base : sl->st;
+    jb.st = st;
     jb.cfg = make_cfg(jb.algo, *jb.opts);
     jb.cfg.variant = variant;
     jb.cfg.ctl_share8 = std::min(8, std::max(0, env_int("SICP_LM_CTL_SHARE", lone ? kLoneCtlShare8 : kBatchCtlShare8)));
@@ -394,14 +436,37 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     jb.lm_grid = lone ? lm_grid_blocks(device) : std::min(gmax, std::max(1, env_int("SICP_LM_GRID", kBatchLmGrid)));
     jb.tm.on = jb.opts->profile != 0;
     jb.trace_ref = fork; jb.trace_id = j;
-    // the clouds may still be building on the stream (or host thread) that created them
-    SICP_CHECK(ensure_built(jb.src, jb.st));
-    SICP_CHECK(ensure_built(jb.tgt, jb.st));
-    jb.tm.begin(SICP_STAGE_COV, jb.st);
-    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, jb.st, lone ? t_helper : nullptr);
-    jb.tm.end(jb.st);
+    // the clouds may still have to be built (deferred), or are building on the stream / host thread that created them
+    SICP_CHECK(ensure_built(jb.src, st));
+    SICP_CHECK(ensure_built(jb.tgt, st));
+    jb.tm.begin(SICP_STAGE_COV, st);
+    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, st, lone ? t_helper : nullptr);
+    jb.tm.end(st);
     SICP_CHECK(r);
-    SICP_CHECK(jb.start(init7s + 7 * (size_t)j));
+    return jb.start(init7s + 7 * (size_t)j);
+  };
+  auto launch = [&](int slot) -> sicp_status {
+    const int j = next++;
+    slot_job[slot] = j;
+    Slot* sl = t_pool.get(slot);
+    cudaStream_t st = lone ? base : sl->st;
+    SICP_CHECK(prepare(j, sl, st));
+    Job& jb = jobs[j];
+    if (pairing && next < nj) {  // take a partner: same stream, its own workspace
+      const int j2 = next++;
+      SICP_CHECK(prepare(j2, t_pool.get(NS + slot), st));
+      jobs[j2].follower = true;
+      jb.partner = &jobs[j2];
+      jb.pair_grid = std::max(3, env_int("SICP_LM_PAIR_GRID", kBatchLmPairGrid));
+    } else if (pairing) {  // odd one out: same kernel, partner slot marked converged
+      Slot* idle = t_pool.get(NS + slot);
+      std::memset(idle->h_ctl, 0, sizeof(RegCtl));
+      idle->h_ctl->pose[3] = 1.0;
+      idle->h_ctl->converged = 1;
+      SICP_CUDA(cudaMemcpyAsync(idle->d_ctl, idle->h_ctl, sizeof(RegCtl), cudaMemcpyHostToDevice, st));
+      jb.idle_partner = idle;
+      jb.pair_grid = std::max(3, env_int("SICP_LM_PAIR_GRID", kBatchLmPairGrid));
+    }
     SICP_CHECK(jb.advance(kChunk));
     live++;
     return SICP_OK;
@@ -410,7 +475,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   const bool hoststat = env_int("SICP_HOSTSTAT", 0) != 0;
   auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_issue = 0, t_wait = 0, t_begin = now_ms(), t0 = t_begin;
-  for (int s = 0; s < S && next < nj && rc == SICP_OK; s++) rc = launch(s);
+  for (int s = 0; s < NS && next < nj && rc == SICP_OK; s++) rc = launch(s);
   t_issue += now_ms() - t0;
   while (live > 0 && rc == SICP_OK) {
     t0 = now_ms();
@@ -421,6 +486,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     if (j < 0) continue;
     if (jobs[j].complete()) {
       jobs[j].finish();
+      if (jobs[j].partner) jobs[j].partner->finish();
       live--;
       slot_job[s] = -1;
       if (next < nj) rc = launch(s);
@@ -432,9 +498,9 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
   if (hoststat)
     fprintf(stderr, "[sicp] run_jobs: %d jobs, %d slots, %.2f ms wall: host issuing %.2f ms, asleep %.2f ms\n", nj, S, now_ms() - t_begin, t_issue, t_wait);
   if (rc != SICP_OK) cudaDeviceSynchronize();  // error path: nothing may still be writing a pinned control block
-  for (int s = 0; s < S; s++) t_pool.get(s)->note.c = nullptr;
+  for (int s = 0; s < (pairing ? 2 * NS : NS); s++) t_pool.get(s)->note.c = nullptr;
   if (!lone) {
-    for (int s = 0; s < S; s++) {  // join: later work on the caller's stream sees the results of every slot
+    for (int s = 0; s < NS; s++) {  // join: later work on the caller's stream sees the results of every slot
       cudaEvent_t e;
       cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
       cudaEventRecord(e, t_pool.get(s)->st);

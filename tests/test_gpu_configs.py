@@ -191,3 +191,34 @@ def test_config5_pose_sweep_batch(sicp, oracle, pkg):
         rot, trans = pkg.synth.pose_error(b["pose"], p["T_gt"])
         ok += rot < 5e-3 and trans < 5e-2
     assert ok >= 0.75 * n_inits  # the convergence basin: most small perturbations come back to the ground truth
+
+
+def test_paired_solves_match_unpaired(sicp, pkg, monkeypatch):
+    """SICP_PAIR=1: two registrations share one LM launch per pass (lm_pair_kernel: the blocks alternate between the two
+    solves, each with its own controller block).  Same pass counts and LM iteration counts as the unpaired batch, poses
+    equal far inside the tolerance, an odd batch size handled (the last job runs against an already-converged dummy), and
+    bit-identical results for identical inputs."""
+    pairs = [pkg.synth.kitti_pair(pair=i, n_points=20_000, n_rings=32, n_az=700) for i in range(5)]
+    opts = sicp.default_options(sicp.ALGO_EM, cm=pairs[0]["cm"])
+    cl = [(sicp.Cloud(q["src_xyz"], q["src_labels"]), sicp.Cloud(q["tgt_xyz"], q["tgt_labels"])) for q in pairs]
+    inits = np.stack([q["init"] for q in pairs])
+    monkeypatch.setenv("SICP_PAIR", "0")
+    plain = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], opts, inits)
+    monkeypatch.setenv("SICP_PAIR", "1")
+    paired = sicp.register_batch(sicp.ALGO_EM, [c[0] for c in cl], [c[1] for c in cl], opts, inits)
+    for a, b in zip(plain, paired):
+        # different block -> partial-sum grouping than the unpaired launch: equal to rounding, not to the bit (compared on
+        # the 7 pose numbers; synth.pose_error's acos has a floor of sqrt(2 ulp) = 2.1e-8 rad)
+        assert np.max(np.abs(np.asarray(a["pose"]) - np.asarray(b["pose"]))) < 1e-9, (a["pose"], b["pose"])
+        assert a["outer_iter"] == b["outer_iter"] and list(a["pass_lm_iters"]) == list(b["pass_lm_iters"])
+    same = sicp.register_batch(sicp.ALGO_EM, [cl[0][0]] * 3, [cl[0][1]] * 3, opts, inits[:1].repeat(3, 0))
+    assert all(np.array_equal(x["pose"], same[0]["pose"]) for x in same)  # pair members and the odd job: same block order, same bits
+    for algo, mk in ((sicp.ALGO_GICP, lambda q: (sicp.Cloud(q["src_xyz"]), sicp.Cloud(q["tgt_xyz"]))),):
+        g = [mk(q) for q in pairs[:4]]
+        gopts = sicp.default_options(algo)
+        monkeypatch.setenv("SICP_PAIR", "0")
+        a4 = sicp.register_batch(algo, [c[0] for c in g], [c[1] for c in g], gopts, inits[:4])
+        monkeypatch.setenv("SICP_PAIR", "1")
+        b4 = sicp.register_batch(algo, [c[0] for c in g], [c[1] for c in g], gopts, inits[:4])
+        for a, b in zip(a4, b4):
+            assert np.max(np.abs(np.asarray(a["pose"]) - np.asarray(b["pose"]))) < 1e-9 and a["outer_iter"] == b["outer_iter"]

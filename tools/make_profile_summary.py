@@ -39,7 +39,8 @@ for r in rows[1:]:
     a[1] += v
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
-    f.write(f"# {tag}: launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` under ncu\n\n")
+    cmd = os.environ.get("PROFILE_CMD", "python bench.py --steps 2 --warmup 1 --no-cpu-baseline")
+    f.write(f"# {tag}: launch list of `{cmd}` under ncu\n\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch device times are cold-cache and serialised;\n"
             "compare SHARES, not absolutes.  Includes warm-up, the device-resident and the host (e2e) legs and the profiled single registration.\n\n")
     f.write("| kernel | launches | total device time (us) | share |\n|---|---:|---:|---:|\n")

@@ -22,3 +22,14 @@ print("knn", sicp.knn(tgt, p["src_xyz"][:100], 20)[0].shape, "fused", sicp.fused
 print("metrics", sicp.label_agreement(src, tgt, p["N"] + 1, pose7=r["pose"])["total"], len(sicp.filter_range(p["src_xyz"], 4.0)), src.transform_f32(r["pose"]).shape)
 src.precompute(20, 1e-3, p["cm"])
 print("getters", src.normals().shape, src.covariances().shape, src.label_vectors().shape, src.self_neighbours().shape)
+# round 2: pass-by-pass path beside the graph loop, pose averaging / fusion, tiny epsilon (the denormal-range Probability gate)
+os.environ["SICP_GRAPH"] = "0"
+r0 = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
+os.environ["SICP_GRAPH"] = "1"
+print("pass-by-pass", r0["outer_iter"], np.array_equal(r0["pose"], r["pose"]))
+from oracle import oracle as O
+poses = np.array([O.se3_plus(r["pose"], np.random.default_rng(i).normal(scale=0.02, size=6)) for i in range(7)])
+print("mean", sicp.iterative_mean(poses, 50)[1], "fusion", sicp.pose_fusion(poses, np.array([np.eye(6) * 1e-4] * 7), r["pose"])[1])
+o6 = sicp.default_options(sicp.ALGO_EM, cm=p["cm"], epsilon=1e-6)
+idx, w, d2 = sicp.correspondences(sicp.ALGO_EM, src, tgt, o6, np.array([0, 0, 0, 1.0, 0, 0, 0.9]))
+print("gate zeroed", int(((idx >= 0) & (w == 0)).sum()))
