@@ -121,17 +121,17 @@ __device__ __forceinline__ void svd3_normal(const double* A, double* normal) {
 #pragma unroll
   for (int i = 0; i < 3; i++) sv[i] *= scale;
   // the column that ends up last after Eigen's descending selection sort
-  int c0 = 0, c1 = 1, c2 = 2;
+  int c1 = 1, c2 = 2;  // columns in places 1 and 2 (place 0 is not needed)
   {  // i = 0: first maximum of (sv0, sv1, sv2)
     int pos = 0; double mx = sv[0];
     if (sv[1] > mx) { mx = sv[1]; pos = 1; }
     if (sv[2] > mx) { mx = sv[2]; pos = 2; }
-    if (mx != 0 && pos != 0) { const double ts = sv[0]; sv[0] = sv[pos]; sv[pos] = ts; if (pos == 1) { c0 = 1; c1 = 0; } else { c0 = 2; c2 = 0; } }
+    if (mx != 0 && pos != 0) { const double ts = sv[0]; sv[0] = sv[pos]; sv[pos] = ts; if (pos == 1) c1 = 0; else c2 = 0; }
     if (mx != 0) {  // i = 1
       if (sv[2] > sv[1] && sv[2] != 0) { const int tc = c1; c1 = c2; c2 = tc; }
     }
   }
-  (void)c0; (void)c1;
+  (void)c1;
   normal[0] = U[c2]; normal[1] = U[3 + c2]; normal[2] = U[6 + c2];
 }
 

@@ -76,8 +76,12 @@ __device__ __forceinline__ bool density_is_zero(double det2pi, double mahal) {
 // together (16-byte loads when the row is 16-byte aligned), which is what hides the gather latency — this kernel
 // moves 261 B per candidate and computes almost nothing.
 constexpr int kEstepThreads = 128;
+#ifndef SICP_ESTEP_MINB
+#define SICP_ESTEP_MINB 4   // resident blocks per SM the register allocation is held to (4: 128 registers, no spills; measured: 5 -> 96
+                            // registers, 0.148 ms per 6 launches, 6 -> 80 registers, 0.142 ms, against 0.130 ms at 4)
+#endif
 template <int KC>
-__global__ void __launch_bounds__(kEstepThreads) estep_kernel(CloudView sv, CloudView tv, int algo, double eps, double gate_d2,
+__global__ void __launch_bounds__(kEstepThreads, SICP_ESTEP_MINB) estep_kernel(CloudView sv, CloudView tv, int algo, double eps, double gate_d2,
                                                               const double* __restrict__ pose7, const int* __restrict__ stop,
                                                               int* __restrict__ corr, const float* __restrict__ d2,
                                                               char* __restrict__ rec, RegCtl* ctl) {
