@@ -100,6 +100,12 @@ __device__ __forceinline__ float box_lb_rn(float qx, float qy, float qz, const f
 //   key = float_bits(d2) << 32 | original_index
 // d2 >= 0, so unsigned order of the bits is numeric order and the 64-bit unsigned compare IS the lexicographic
 // (d2, original index) order of the exact-kNN contract — no separate tie-break path.
+#ifndef SICP_PHASE1_FMA
+#define SICP_PHASE1_FMA 1
+#endif
+#ifndef SICP_TOPK_F64CMP
+#define SICP_TOPK_F64CMP 1
+#endif
 template <int K>
 struct TopK {
   unsigned long long key[K];
@@ -118,12 +124,27 @@ struct TopK {
     // the previous worst falls off the end
     unsigned long long carry = k;
 #pragma unroll
-    for (int i = 0; i < K; i++) {
-      const unsigned long long cur = key[i];
-      const bool lt = carry < cur;
-      key[i] = lt ? carry : cur;
-      carry = lt ? cur : carry;
-    }
+    for (int i = 0; i < K; i++) cmpxchg(key[i], carry);
+  }
+  // slot <- min(slot, carry), carry <- max(slot, carry).  The integer form costs 4 ISETP + 4 SEL per step, all on the
+  // half-rate ALU pipe, which is what bounds the k = 20 search (ncu: 60 % of its instructions are this chain).  Keys
+  // are bit patterns of FINITE NON-NEGATIVE doubles (high word = float bits of d2 <= 0x7f800000 < 0x7ff00000, sign
+  // clear; the early-out above keeps NaN distances out), whose numeric order is their unsigned order, denormals
+  // included (f64 never flushes) — so ONE f64 compare on the otherwise idle FP64 pipe decides the step and the ALU
+  // pipe is left with the 4 selects.
+  static __device__ __forceinline__ void cmpxchg(unsigned long long& slot, unsigned long long& carry) {
+#if SICP_TOPK_F64CMP
+    unsigned long long lo, hi;
+    asm("{\n\t.reg .pred p;\n\t.reg .f64 a, b;\n\tmov.b64 a, %2;\n\tmov.b64 b, %3;\n\tsetp.lt.f64 p, b, a;\n\t"
+        "selp.b64 %0, %3, %2, p;\n\tselp.b64 %1, %2, %3, p;\n\t}"
+        : "=&l"(lo), "=&l"(hi) : "l"(slot), "l"(carry));  // early-clobber: the second select still reads both inputs
+    slot = lo; carry = hi;
+#else
+    const unsigned long long cur = slot;
+    const bool lt = carry < cur;
+    slot = lt ? carry : cur;
+    carry = lt ? cur : carry;
+#endif
   }
 };
 
@@ -275,12 +296,27 @@ __device__ __forceinline__ void knn_search(const CloudView& tv, const Segment& s
       for (int h = 0; h < kSplit; h++) {
         unsigned pass = 0;
         if (valid) {
+#if SICP_PHASE1_FMA
+          // phase 1 only FILTERS (phase 2 recomputes the contract's d2 and compares the full key), so it may use the
+          // contracted form (3 FADD + FMUL + 2 FFMA instead of 5 FADD + 3 FMUL on the pipe that bounds this loop) against a
+          // threshold inflated by far more than the two forms can differ: both are within 2^-22 relative of the real sum of
+          // squares of the SAME rounded differences (plus a few 2^-149 when products are denormal, covered by FLT_MIN).
+          const float w0 = __fmaf_rn(L.worst(), 1.0f + 1.0f / 262144.0f, 1.17549435e-38f);
+#pragma unroll
+          for (int j = 0; j < kPart; j++) {
+            const float4 p = ws.leaf[h * kPart + j];
+            const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+            const float dj = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            pass |= (dj <= w0 ? 1u : 0u) << j;
+          }
+#else
           const float w0 = L.worst();
 #pragma unroll
           for (int j = 0; j < kPart; j++) {
             const float dj = dist2_rn(qx, qy, qz, ws.leaf[h * kPart + j]);
             pass |= (dj <= w0 ? 1u : 0u) << j;
           }
+#endif
         }
 #ifdef SICP_STATS
         { const unsigned mx = __reduce_max_sync(kFull, (unsigned)__popc(pass)); SICP_STAT(3, mx); }
