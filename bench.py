@@ -333,6 +333,17 @@ def main():
                                    "stages of concurrent registrations overlap in the batch itself",
                     "note": "working set of one pair is L2-resident; DRAM traffic is far below algorithmic bytes (see profiles/)",
                     "kernels": kernels}
+        if "lm" in kernels:
+            # The LM sweep is bound by the FP64 pipe, not by HBM (the contract's "bound" has no value for that): 136 FP64
+            # warp-instructions per residual evaluation (ncu: inst_executed_pipe_fp64 / residual evaluations)
+            # against the pipe's issue rate of one warp-instruction per 2.2 cycles per scheduler (tools/ubench/fp64_pipes.cu).
+            sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+            pipe_peak = 148 * 4 * 32 / 2.2 * sm_hz
+            lm_rate = 136.0 * units["lm"] / (kernels["lm"]["ms_total"] * 1e-3)
+            roofline["secondary"] = {"kernel": "lm_kernel", "bound": "fp64 pipe", "achieved": round(lm_rate / 1e12, 3), "peak": round(pipe_peak / 1e12, 3),
+                                     "unit": "T FP64 thread-instructions/s", "frac": round(lm_rate / pipe_peak, 4),
+                                     "note": "lone solve on 148 CTAs (control gaps included); the batch configuration (37 CTAs per solve, 8 solves in flight) "
+                                             "runs the pipe at 50.4 % (profiles/r2_ncu_lm_batch.md)"}
         # secondary metric of BASELINE.json: exact kNN queries/s (120k transformed source points against the 120k target tree)
         knn_qps = {}
         s = sicp.Cloud(p0["src_xyz"], p0["src_labels"], device=local_rank)

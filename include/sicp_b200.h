@@ -104,8 +104,11 @@ uint64_t sicp_launch_count(void);
  * sicp_cloud_create replaces GICP::setSourceCloud/setTargetCloud (gicp.h:42-63), Em...::set*Cloud
  * (em_icp.h:50-66) [layout WHOLE] and pcl_2_semantic + SemanticPointCloud::addSemanticCloud's kd-tree build
  * (pcl_2_semantic.h:14-42, impl/semantic_point_cloud.hpp:17-23) [layout PER_CLASS: the first-appearance label
- * partition runs on the device]: it uploads the points into device SoA buffers and builds the Morton-sorted search tree(s).  xyz points to the first x; consecutive points
- * are xyz_stride bytes apart (12 packed, 16 pcl::PointXYZ, 32 pcl::PointXYZL).  labels may be NULL (GICP).     */
+ * partition runs on the device]: it copies the points to the device (the host buffers may be reused as soon as
+ * the call returns) and builds the Z-order-sorted search tree(s).  For layout WHOLE the sort and tree build are
+ * deferred to the first call that needs them (a registration, a search, a getter) and run on that call's stream;
+ * SICP_EAGER_BUILD=1 builds at once.  xyz points to the first x; consecutive points are xyz_stride bytes apart
+ * (12 packed, 16 pcl::PointXYZ, 32 pcl::PointXYZL).  labels may be NULL (GICP).  At most 2^26 points.           */
 sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* labels, size_t label_stride, size_t n,
                               int layout, int device, sicp_cloud** out);
 /* Same, inputs already resident in HBM: d_xyz is packed n*3 float32, d_labels n uint32 (or NULL). */

@@ -42,7 +42,10 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w") as f:
     cmd = os.environ.get("PROFILE_CMD", "python bench.py --steps 2 --warmup 1 --no-cpu-baseline")
     f.write(f"# {tag}: launch list of `{cmd}` under ncu\n\n")
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch device times are cold-cache and serialised;\n"
-            "compare SHARES, not absolutes.  Includes warm-up, the device-resident and the host (e2e) legs and the profiled single registration.\n\n")
+            "compare SHARES, not absolutes.  Includes warm-up, the device-resident and the host (e2e) legs and the profiled single registration.\n"
+            "The batch legs launch each LM solve on 37 CTAs (sized for 8 registrations in flight); ncu serialises the launches, so an LM launch\n"
+            "runs alone on a quarter of the GPU and its share here (≈ 64 %) is above the live one (bench.py's per-stage events of a lone\n"
+            "registration on 148 CTAs: LM ≈ 54 % of the four stages; marginal cost inside a batch, tools/sweep.py: ≈ 40 %).\n\n")
     f.write("| kernel | launches | total device time (us) | share |\n|---|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% |\n")
