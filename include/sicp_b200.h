@@ -104,8 +104,10 @@ uint64_t sicp_launch_count(void);
  * sicp_cloud_create replaces GICP::setSourceCloud/setTargetCloud (gicp.h:42-63), Em...::set*Cloud
  * (em_icp.h:50-66) [layout WHOLE] and pcl_2_semantic + SemanticPointCloud::addSemanticCloud's kd-tree build
  * (pcl_2_semantic.h:14-42, impl/semantic_point_cloud.hpp:17-23) [layout PER_CLASS: the first-appearance label
- * partition runs on the device]: it copies the points to the device (the host buffers may be reused as soon as
- * the call returns) and builds the Z-order-sorted search tree(s).  For layout WHOLE the sort and tree build are
+ * partition runs on the device]: it copies the points to the device (pageable host buffers may be reused as soon
+ * as the call returns; from page-locked buffers the copy is asynchronous on the calling thread's stream, so they
+ * must stay unchanged until a call that consumes the cloud has returned — the reference shares the caller's
+ * cloud until align() in the same way) and builds the Z-order-sorted search tree(s).  For layout WHOLE the sort and tree build are
  * deferred to the first call that needs them (a registration, a search, a getter) and run on that call's stream;
  * SICP_EAGER_BUILD=1 builds at once.  xyz points to the first x; consecutive points are xyz_stride bytes apart
  * (12 packed, 16 pcl::PointXYZ, 32 pcl::PointXYZL).  labels may be NULL (GICP).  At most 2^26 points.           */

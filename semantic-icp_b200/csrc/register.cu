@@ -207,7 +207,26 @@ struct SlotPool {
   ~SlotPool() { for (Slot* s : slots) { s->destroy(); delete s; } }
 };
 static thread_local SlotPool t_pool;
-static thread_local cudaStream_t t_helper = nullptr;  // target covariances of a lone registration
+// second stream of a lone registration (target build + covariances beside the source's); owned per host thread and device
+struct HelperStream {
+  int device = -1;
+  cudaStream_t st = nullptr;
+  sicp_status ensure(int dev) {
+    if (st && device == dev) return SICP_OK;
+    release();
+    SICP_CUDA(cudaSetDevice(dev));
+    SICP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    device = dev;
+    return SICP_OK;
+  }
+  void release() {
+    if (st && cudaSetDevice(device) == cudaSuccess) cudaStreamDestroy(st);
+    cudaGetLastError();  // context already gone at process exit: nothing to free
+    st = nullptr; device = -1;
+  }
+  ~HelperStream() { release(); }
+};
+static thread_local HelperStream t_helper;
 
 // graph path switch: SICP_GRAPH=0 disables it; it also turns itself off for the process if the driver rejects the graph
 static std::atomic<int> g_graph_ok{1};
@@ -410,7 +429,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     SICP_CHECK(sl->ensure(device, nc_max));
     sl->note = SlotNote{&done_q, s};
   }
-  if (lone && !t_helper) SICP_CUDA(cudaStreamCreateWithFlags(&t_helper, cudaStreamNonBlocking));
+  if (lone) SICP_CHECK(t_helper.ensure(device));
   if (!lone) {
     SICP_CUDA(cudaEventCreate(&fork));
     SICP_CUDA(cudaEventRecord(fork, base));
@@ -440,7 +459,7 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     SICP_CHECK(ensure_built(jb.src, st));
     SICP_CHECK(ensure_built(jb.tgt, st));
     jb.tm.begin(SICP_STAGE_COV, st);
-    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, st, lone ? t_helper : nullptr);
+    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, st, lone ? t_helper.st : nullptr);
     jb.tm.end(st);
     SICP_CHECK(r);
     return jb.start(init7s + 7 * (size_t)j);

@@ -7,6 +7,16 @@ sicp, synth = pkg.sicp, pkg.synth
 p = synth.room_pair(seed=5, n_points=3000)
 src, tgt = sicp.Cloud(p["src_xyz"], p["src_labels"]), sicp.Cloud(p["tgt_xyz"], p["tgt_labels"])
 opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
+if os.environ.get("SAN_STAGES") == "search":  # searches, covariances, first-pass correspondences only (minutes faster under memcheck)
+    for k in (1, 4, 20):
+        print("knn", k, sicp.knn(tgt, p["src_xyz"], k, pose7=p["init"])[0].shape)
+    src.precompute(20, 1e-3, p["cm"])
+    c2 = sicp.Cloud(p["src_xyz"], p["src_labels"], layout=sicp.CLOUD_PER_CLASS)
+    c2.precompute(20, 1e-3)
+    print("getters", src.normals().shape, src.label_vectors().shape, src.self_neighbours().shape, c2.covariances().shape)
+    idx, w, d2 = sicp.correspondences(sicp.ALGO_EM, src, tgt, opts, p["init"])
+    print("corr", int((idx >= 0).sum()), float(w.sum()))
+    sys.exit(0)
 r = sicp.register(sicp.ALGO_EM, src, tgt, opts, p["init"])
 print("em", r["outer_iter"], r["lm_iters_total"])
 g = sicp.register(sicp.ALGO_GICP, sicp.Cloud(p["src_xyz"]), sicp.Cloud(p["tgt_xyz"]), sicp.default_options(sicp.ALGO_GICP), p["init"])
