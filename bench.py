@@ -168,11 +168,26 @@ def run_reference(args, rank, world):
                                    "(oracle restatement, OpenMP on all host threads)"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
+
+
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+# NCCL_DEBUG=VERSION is set on the box), so fd 1 is pointed at stderr for the whole run and the line is written to the
+# saved descriptor.
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -431,7 +446,7 @@ def main():
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "ms_per_step_by_rank": ms_dev_by_rank, "records_gathered": int(records.shape[0]), "knn_queries_per_s": knn_qps, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
