@@ -268,6 +268,36 @@ __device__ __forceinline__ double log_ge1(double x) {
   return dk * 6.93147180369123816490e-01 - ((hfsq - (ss * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
 }
 
+// log(x) for normal x >= 1 through a 256-entry table in shared memory (fill_log_table): x = 2^k m, m in [1, 2); entry i
+// covers m in [1 + i/256, 1 + (i+1)/256) with c_i = 1 / midpoint and L_i = -log(c_i), so log(m) = L_i + log1p(r),
+// r = m c_i - 1, |r| <= 2^-9, and a degree-6 series is exact to 2^-63 / 7.  12 FP64 instructions against the 26 of
+// log_ge1 (no reciprocal, short polynomial): the loss is a third of the sweep's FP64 work.  Absolute error ~1e-16.
+#ifndef SICP_LM_LOGTAB
+#define SICP_LM_LOGTAB 1
+#endif
+constexpr int kLogTab = 256;
+__device__ __forceinline__ void fill_log_table(double2* tab, int tid, int nthreads) {
+  for (int i = tid; i < kLogTab; i += nthreads) {
+    const double c = 1.0 / (1.0 + (i + 0.5) * (1.0 / kLogTab));
+    tab[i] = make_double2(c, -log(c));
+  }
+}
+__device__ __forceinline__ double log_tab(double x, const double2* __restrict__ tab) {
+  const int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  const int k = (hi >> 20) - 1023;
+  const double2 t = tab[(hi >> 12) & (kLogTab - 1)];
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+  const double r = fma(m, t.x, -1.0);
+  double q = fma(r, -1.0 / 6.0, 0.2);
+  q = fma(r, q, -0.25);
+  q = fma(r, q, 1.0 / 3.0);
+  q = fma(r, q, -0.5);
+  const double dk = (double)k;
+  const double small = fma(r * r, q, fma(dk, 1.90821492927058770002e-10, r));  // r^2 q + k ln2_lo + r
+  return fma(dk, 6.93147180369123816490e-01, t.y + small);                    // k ln2_hi is exact (21 trailing zero bits)
+}
+
 // T * exp(delta) (local_parameterization_se3.h:22) on the LM critical path: one sincos, reciprocal multiplies and an
 // rsqrt renormalisation instead of the divisions / square roots of the general-purpose se3.cuh routines.
 __device__ __forceinline__ void pose_plus_fast(const double* x7, const double* d, double* out7) {
@@ -523,11 +553,16 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 // rho(s), rho'(s) at s = res^2 of the three Ceres loss compositions, multiplied by the weight w (the
 // E-step weight for EM; exactly 1.0 or 0.0 for GICP / SemanticICP, where 0 marks "no residual in this record").
 template <int ALGO>
-__device__ __forceinline__ void loss_fast(double w, double res, double* rho0, double* rho1) {
+__device__ __forceinline__ void loss_fast(double w, double res, const double2* __restrict__ logtab, double* rho0, double* rho1) {
+#if SICP_LM_LOGTAB
+#define SICP_LOG_GE1(x) log_tab((x), logtab)
+#else
+#define SICP_LOG_GE1(x) log_ge1(x)
+#endif
   const double s = res * res;
   if (ALGO == SICP_ALGO_SEMANTIC) {  // CauchyLoss(1.5)
     const double sum = 1.0 + s * (1.0 / 2.25);
-    *rho0 = w * (2.25 * log_ge1(sum));
+    *rho0 = w * (2.25 * SICP_LOG_GE1(sum));
     *rho1 = w * fmax(DBL_MIN, rcp_pos(sum));
     return;
   }
@@ -536,7 +571,7 @@ __device__ __forceinline__ void loss_fast(double w, double res, double* rho0, do
   const double rs = rsqrt_pos(v);
   const double g0 = v * rs;
   const double sum = 1.0 + g0 * (1.0 / 9.0);
-  const double f0 = w * (9.0 * log_ge1(sum)), f1 = w * fmax(DBL_MIN, rcp_pos(sum));
+  const double f0 = w * (9.0 * SICP_LOG_GE1(sum)), f1 = w * fmax(DBL_MIN, rcp_pos(sum));
   *rho0 = f0;
   *rho1 = f1 * (0.5 * rs);
 }
@@ -599,7 +634,8 @@ __device__ __forceinline__ const char* first_block(const char* rec, int g0, int 
 // next_src: first block of the sweep this warp will run NEXT (same problem, or the other one of a pair): prefetched as this
 // sweep ends.
 template <int ALGO, int KC, int THREADS>
-__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, double* acc, GroupPipe& pp, int g0, int g1, const char* next_src) {
+__device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, const double2* __restrict__ logtab, double* acc, GroupPipe& pp, int g0, int g1,
+                                          const char* next_src) {
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
   constexpr unsigned GB = Rec::group_bytes(KC);
@@ -657,7 +693,7 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, d
       for (int i = 0; i < 3; i++) b[i] = 0.5 * d[i] + (g1c * u[i] + g2c * m[i]);
       const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
       double rho0, rho1;
-      loss_fast<ALGO>(w, res, &rho0, &rho1);
+      loss_fast<ALGO>(w, res, logtab, &rho0, &rho1);
       const double mb = a.cfg.kappa * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]);
       const double v[3] = {q0[0] - mb * m[0], q0[1] - mb * m[1], q0[2] - mb * m[2]};
       double j[6], jw[6];
@@ -812,6 +848,8 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
   __shared__ double s_x[8];  // pose to evaluate [7] + done flag
   __shared__ double s_RT[12];  // its rotation matrix (row-major) and translation
   __shared__ double s_L[36];   // Cholesky factor scratch of lm_control_warp
+  __shared__ double2 s_logtab[kLogTab];  // log_tab's (c_i, -log c_i)
+  fill_log_table(s_logtab, threadIdx.x, THREADS);
   LMSync* sy = a.sync;
   const bool eval_only = a.eval_pose != nullptr;
   const bool controller = blockIdx.x == 0;
@@ -851,7 +889,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
     }
     __syncthreads();
     double acc[kAcc];
-    sweep_acc<ALGO, KC, THREADS>(a, s_RT, acc, pp, g0, g1, eval_only ? nullptr : my_first);
+    sweep_acc<ALGO, KC, THREADS>(a, s_RT, s_logtab, acc, pp, g0, g1, eval_only ? nullptr : my_first);
     block_reduce<THREADS>(acc, s_acc, a.partials);
     gen++;
     __syncthreads();  // the block's partial sums are written; thread 0's gpu-scope fence below is cumulative over them
@@ -954,6 +992,8 @@ __global__ void __launch_bounds__(THREADS, 1) lm_pair_kernel(LMPairArgs pa) {
   __shared__ double s_x[2][8];  // per problem: pose to evaluate [7] + done flag
   __shared__ double s_RT[12];
   __shared__ double s_L[36];
+  __shared__ double2 s_logtab[kLogTab];
+  fill_log_table(s_logtab, threadIdx.x, THREADS);
   const int nsweep = (int)gridDim.x - 2;
   if (threadIdx.x < 16) {
     const int p = threadIdx.x >> 3, i = threadIdx.x & 7;
@@ -1064,7 +1104,7 @@ __global__ void __launch_bounds__(THREADS, 1) lm_pair_kernel(LMPairArgs pa) {
       double acc[kAcc];
       // what this warp reads next: the other problem's first block while that problem is still running, else this one's again
       const char* next_src = !done[1 - p] ? first[1 - p] : first[p];
-      sweep_acc<ALGO, KC, THREADS>(a, s_RT, acc, pp, g0[p], g1[p], next_src);
+      sweep_acc<ALGO, KC, THREADS>(a, s_RT, s_logtab, acc, pp, g0[p], g1[p], next_src);
       block_reduce<THREADS>(acc, s_acc, a.partials);
       gen[p]++;
       __syncthreads();
