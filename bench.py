@@ -349,13 +349,13 @@ def main():
                     "note": "working set of one pair is L2-resident; DRAM traffic is far below algorithmic bytes (see profiles/)",
                     "kernels": kernels}
         if "lm" in kernels:
-            # The LM sweep is bound by the FP64 pipe, not by HBM (the contract's "bound" has no value for that): 123 FP64-pipe
-            # warp-instructions per residual evaluation (SASS of the sweep loop: 477 DFMA/DMUL/DADD + 15 F2F per 4 residuals;
-            # ncu's inst_executed_pipe_fp64 gave 136 = 544 / 4 for the loop before the table log) against the
+            # The LM sweep is bound by the FP64 pipe, not by HBM (the contract's "bound" has no value for that): 115 FP64-pipe
+            # warp-instructions per residual evaluation (SASS of the sweep loop: 445 DFMA/DMUL/DADD + 15 F2F per 4 residuals;
+            # ncu's inst_executed_pipe_fp64 gave 136 = 544 / 4 for the loop of round 2's first half) against the
             # pipe's issue rate of one warp-instruction per 2.2 cycles per scheduler (tools/ubench/fp64_pipes.cu).
             sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
             pipe_peak = 148 * 4 * 32 / 2.2 * sm_hz
-            lm_rate = 123.0 * units["lm"] / (kernels["lm"]["ms_total"] * 1e-3)
+            lm_rate = 115.0 * units["lm"] / (kernels["lm"]["ms_total"] * 1e-3)
             roofline["secondary"] = {"kernel": "lm_kernel", "bound": "fp64 pipe", "achieved": round(lm_rate / 1e12, 3), "peak": round(pipe_peak / 1e12, 3),
                                      "unit": "T FP64 thread-instructions/s", "frac": round(lm_rate / pipe_peak, 4),
                                      "note": "lone solve on 148 CTAs (control gaps included); the batch configuration (37 CTAs per solve, 8 solves in flight) "

@@ -245,6 +245,21 @@ __device__ __forceinline__ double rsqrt_pos(double a) {
   e = fma(-h * y, y, 0.5);
   return fma(y, e, y);
 }
+// One third-order step instead of two Newton steps.  The MUFU seeds read only the top 20 mantissa bits of the argument, so
+// their relative error e is <= ~2^-20 and the remainder e^3 ~ 2^-60 is below the rounding of the result: same accuracy
+// class (<= 1 ulp) for one FP64 instruction less (rcp) or two less (rsqrt).  Used by the residual sweep only.
+__device__ __forceinline__ double rcp_pos3(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  const double e = fma(-a, x, 1.0);          // 1/a = x / (1 - e) = x (1 + e + e^2 + ...)
+  return fma(x, fma(e, e, e), x);
+}
+__device__ __forceinline__ double rsqrt_pos3(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double e = fma(-(a * y), y, 1.0);    // a y^2 = 1 - e;  a^-1/2 = y (1 - e)^-1/2 = y (1 + e/2 + 3 e^2/8 + ...)
+  return fma(y, e * fma(0.375, e, 0.5), y);
+}
 // log(x) for normal x >= 1 (fdlibm e_log.c reduction and minimax coefficients; error < 1 ulp)
 __device__ __forceinline__ double log_ge1(double x) {
   int hi = __double2hiint(x);
@@ -563,15 +578,15 @@ __device__ __forceinline__ void loss_fast(double w, double res, const double2* _
   if (ALGO == SICP_ALGO_SEMANTIC) {  // CauchyLoss(1.5)
     const double sum = 1.0 + s * (1.0 / 2.25);
     *rho0 = w * (2.25 * SICP_LOG_GE1(sum));
-    *rho1 = w * fmax(DBL_MIN, rcp_pos(sum));
+    *rho1 = w * fmax(DBL_MIN, rcp_pos3(sum));
     return;
   }
   // ComposedLoss(CauchyLoss(3.0) [ScaledLoss w for EM], SQLoss): g = sqrt(s + eps), f = 9 log(1 + g/9)
   const double v = s + DBL_EPSILON;
-  const double rs = rsqrt_pos(v);
+  const double rs = rsqrt_pos3(v);
   const double g0 = v * rs;
   const double sum = 1.0 + g0 * (1.0 / 9.0);
-  const double f0 = w * (9.0 * SICP_LOG_GE1(sum)), f1 = w * fmax(DBL_MIN, rcp_pos(sum));
+  const double f0 = w * (9.0 * SICP_LOG_GE1(sum)), f1 = w * fmax(DBL_MIN, rcp_pos3(sum));
   *rho0 = f0;
   *rho1 = f1 * (0.5 * rs);
 }
@@ -609,8 +624,9 @@ struct GroupPipe {
 //   d = p_t - (R p_s + t),  m = R n_s,  b = (2I - kappa(n_t n_t^T + m m^T))^-1 d,  res = d.b
 //   local 6-dof Jacobian of res for T*exp(delta):  J = -2 D j,  j = [b ; v x b],  v = R p_s - kappa (m.b) m,
 //   D = blockdiag(R^T, R^T)                     (equals J_ups = -2c, J_om = 2c x (p_s + C_s c), c = R^T b)
-// The thread accumulates  A_H += rho' j j^T (lower triangle),  A_g += rho' res j,  A_c += rho;  the constant factors
-// (4, -2, 1/2) and the rotation D are applied ONCE to the 28 grid totals by the controller block.
+// The thread carries 2j (b2 = 2b: one FMA less per component, exact scaling) and accumulates  A_H += rho' (2j)(2j)^T
+// (lower triangle),  A_g += rho' res (2j),  A_c += rho;  the remaining constants (sign of g, 1/2 of the cost) and the
+// rotation D are applied ONCE to the 28 grid totals by the controller block (rotate_totals).
 // The KC records of a slot are evaluated by straight-line, branch-free code (records without a residual have w = 0 and
 // zeroed geometry) so that their dependency chains interleave.
 // Data movement: a warp-iteration covers one GROUP of 32 slots, whose records are one contiguous block (struct Rec).
@@ -653,6 +669,7 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, c
     if (want && lane == 0) bulk_load(smem_u32(pp.buf + (pp.uses & 1) * GB), want, GB, pp.bar + 8 * (pp.uses & 1));
   }
   pp.primed_src = nullptr;
+  const double aa2 = a.cfg.aa * a.cfg.aa;
   for (int g = gfirst; g < g1; g += W) {
     __syncwarp();  // every lane is done with the buffer the next copy lands in (it was read one iteration ago)
     if (lane == 0 && g + W < g1) bulk_load(smem_u32(pp.buf + ((pp.uses + 1) & 1) * GB), rec + (size_t)(g + W) * GB, GB, pp.bar + 8 * ((pp.uses + 1) & 1));
@@ -685,16 +702,18 @@ __device__ __forceinline__ void sweep_acc(const LMArgs& a, const double* s_RT, c
       const double cuv = u[0] * m[0] + u[1] * m[1] + u[2] * m[2];
       const double pu = u[0] * d[0] + u[1] * d[1] + u[2] * d[2];
       const double pm = m[0] * d[0] + m[1] * d[1] + m[2] * d[2];
+      // carried as b2 = 2 b (scaling by 2 is exact): b2 = d + 2 g1 u + 2 g2 m is two FMAs per component, and the factor
+      // moves into the constants (hk = 2 k4 here, hk = kappa / 2 for m.b below, 1 and -1 instead of 4 and -2 in rotate_totals)
       const double be = a.cfg.hk * cuv;
-      const double idet = a.cfg.k4 * rcp_pos((a.cfg.aa - be) * (a.cfg.aa + be));
+      const double idet = a.cfg.hk * rcp_pos3(fma(-be, be, aa2));          // (aa - be)(aa + be) = aa^2 - be^2
       const double g1c = (a.cfg.aa * pu + be * pm) * idet, g2c = (be * pu + a.cfg.aa * pm) * idet;
       double b[3];
 #pragma unroll
-      for (int i = 0; i < 3; i++) b[i] = 0.5 * d[i] + (g1c * u[i] + g2c * m[i]);
-      const double res = d[0] * b[0] + d[1] * b[1] + d[2] * b[2];
+      for (int i = 0; i < 3; i++) b[i] = fma(g1c, u[i], fma(g2c, m[i], d[i]));
+      const double res = 0.5 * (d[0] * b[0] + d[1] * b[1] + d[2] * b[2]);
       double rho0, rho1;
       loss_fast<ALGO>(w, res, logtab, &rho0, &rho1);
-      const double mb = a.cfg.kappa * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]);
+      const double mb = a.cfg.hk * (m[0] * b[0] + m[1] * b[1] + m[2] * b[2]);
       const double v[3] = {q0[0] - mb * m[0], q0[1] - mb * m[1], q0[2] - mb * m[2]};
       double j[6], jw[6];
       j[0] = b[0]; j[1] = b[1]; j[2] = b[2];
@@ -779,7 +798,8 @@ __device__ __forceinline__ void reduce_partials(const double* part, double (*s_r
 }
 
 // Grid totals (A_H, A_g, A_c) -> Ceres quantities in the local frame of the evaluated pose:
-//   H = 4 D A_H D^T,  g = -2 D A_g,  cost = A_c / 2,  D = blockdiag(R^T, R^T).  28 threads, one output each.
+//   H = D A_H D^T,  g = -D A_g,  cost = A_c / 2,  D = blockdiag(R^T, R^T)  (the sweep accumulates with 2j, so the 4 and -2
+//   of J = -2 D j are already inside A_H and A_g).  28 threads, one output each.
 __device__ __forceinline__ void rotate_totals(const double* s_tot, const double* R, double* s_rot) {
   const int e = threadIdx.x;
   if (e < 21) {
@@ -790,12 +810,12 @@ __device__ __forceinline__ void rotate_totals(const double* s_tot, const double*
     double s = 0;
     for (int k = 0; k < 3; k++)
       for (int l = 0; l < 3; l++) s += R[3 * k + i] * s_tot[tri(3 * A + k, 3 * B + l)] * R[3 * l + jx];
-    s_rot[e] = 4.0 * s;
+    s_rot[e] = s;
   } else if (e < 27) {
     const int a = e - 21, A = a / 3, i = a % 3;
     double s = 0;
     for (int k = 0; k < 3; k++) s += R[3 * k + i] * s_tot[21 + 3 * A + k];
-    s_rot[e] = -2.0 * s;
+    s_rot[e] = -s;
   } else if (e == 27) {
     s_rot[27] = 0.5 * s_tot[27];
   }
