@@ -359,7 +359,8 @@ def main():
             roofline["secondary"] = {"kernel": "lm_kernel", "bound": "fp64 pipe", "achieved": round(lm_rate / 1e12, 3), "peak": round(pipe_peak / 1e12, 3),
                                      "unit": "T FP64 thread-instructions/s", "frac": round(lm_rate / pipe_peak, 4),
                                      "note": "lone solve on 148 CTAs (control gaps included); the batch configuration (37 CTAs per solve, 8 solves in flight) "
-                                             "runs the pipe at 50.4 % (profiles/r2_ncu_lm_batch.md)"}
+                                             "showed 50.6 % of the pipe with 544 FP64-pipe instructions per 4 residuals and shows 45.7 % with the final 460 "
+                                             "(same solve, 7 % faster; profiles/r2_ncu_lm_batch.md)"}
         # secondary metric of BASELINE.json: exact kNN queries/s (120k transformed source points against the 120k target tree)
         knn_qps = {}
         s = sicp.Cloud(p0["src_xyz"], p0["src_labels"], device=local_rank)
