@@ -34,7 +34,7 @@ struct LMConfig {
   int variant;           // shape of the LM kernel (lm.cu: kLmShapes)
   int ctl_share8;        // sweep share of the LM controller block in eighths of a normal block's share (0..8)
 };
-constexpr int kLmVariants = 2;
+constexpr int kLmVariants = 5;
 constexpr int kLmMaxGrid = 320;       // block partials reserved per workspace
 constexpr int kLmSyncDoubles = 32;    // LMSync lives in front of the partials
 constexpr size_t kLmPartialsDoubles = kLmSyncDoubles + (size_t)kLmMaxGrid * 28;

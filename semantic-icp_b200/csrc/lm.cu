@@ -855,8 +855,8 @@ __device__ __forceinline__ bool finish_pass(RegCtl* c, const LMState& S, const L
 // ONE 256-thread CTA per SM: with up to 255 registers per thread the k_c residual chains of a slot interleave without
 // spills, which feeds the FP64 pipe better than twice the warps at 128 registers (measured: 1.97 -> 1.76 ms of LM per
 // KITTI EM registration), and every CTA sees the same SM so none finishes early behind an older neighbour.
-template <int ALGO, int KC, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
+template <int ALGO, int KC, int THREADS>
+__device__ __forceinline__ void lm_body(const LMArgs& a) {
   extern __shared__ __align__(128) unsigned char s_dyn[];
   double* s_acc = reinterpret_cast<double*>(s_dyn);                          // [kAcc][THREADS] block_reduce staging
   char* s_pipe = reinterpret_cast<char*>(s_dyn) + sizeof(double) * kAcc * THREADS;  // [THREADS/32][2][group bytes] record double buffers
@@ -986,6 +986,17 @@ __global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
     a.ctl->dbg_cycles[4] += t_red;
     a.ctl->dbg_cycles[6] += t_lm;
   }
+}
+template <int ALGO, int KC, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) lm_kernel(LMArgs a) {
+  lm_body<ALGO, KC, THREADS>(a);
+}
+// The same solve held to REGS registers per thread (256-thread CTA).  At ~240 registers the CTA owns the SM's whole
+// register file; capped lower, the searches and E-steps of the other registrations of a batch can run beside it on
+// the SM's idle issue slots (the sweep issues on ~35 % of the cycles and is bound by the FP64 pipe and its own latencies).
+template <int ALGO, int KC, int REGS>
+__global__ void __maxnreg__(REGS) lm_kernel_capped(LMArgs a) {
+  lm_body<ALGO, KC, 256>(a);
 }
 
 // ------------------------------------------------------------------ K4 + K5 for TWO registrations at once
@@ -1294,15 +1305,18 @@ __global__ void pose_fusion_kernel(const double* __restrict__ pinv7s, const doub
 
 // ------------------------------------------------------------------ host launchers
 // Shapes of the LM kernel (LMConfig.variant).  0 is the lone-registration shape: one 256-thread CTA per SM with every
-// record chain of a slot interleaved (~240 registers).  The others trade per-solve speed for co-residency: a CTA that
-// leaves registers free lets the CTAs of OTHER registrations (a second solve in its control step, kNN kernels) use the
-// SM while this one waits — what a batch needs.
+// record chain of a slot interleaved (~240 registers, the SM's whole register file).  1: 128-thread CTAs.  2-4: the
+// 256-thread CTA held to 176 / 160 / 144 registers (no or a few bytes of spills): less interleave per warp, but the
+// kernels of OTHER registrations become co-resident with the solve — what a batch wants (register.cu: kBatchLmVariant).
 struct LmShape { int threads, minb; };
-static const LmShape kLmShapes[kLmVariants] = {{256, 1}, {128, 1}};
+static const LmShape kLmShapes[kLmVariants] = {{256, 1}, {128, 1}, {256, 1}, {256, 1}, {256, 1}};
 template <int ALGO, int KC>
 static void* lm_entry_algo(int variant) {
   switch (variant) {
     case 1: return (void*)lm_kernel<ALGO, KC, 128, 1>;
+    case 2: return (void*)lm_kernel_capped<ALGO, KC, 176>;
+    case 3: return (void*)lm_kernel_capped<ALGO, KC, 160>;
+    case 4: return (void*)lm_kernel_capped<ALGO, KC, 144>;
     default: return (void*)lm_kernel<ALGO, KC, 256, 1>;
   }
 }

@@ -30,7 +30,8 @@ namespace sicp {
 // Batch defaults (tuned on one B200; the environment variables of the same purpose override them for
 // tuning runs): registrations in flight, LM kernel shape and LM grid of a solve that shares the GPU.
 constexpr int kBatchConcurrent = 8;
-constexpr int kBatchLmVariant = 0;
+constexpr int kBatchLmVariant = 3;  // 256-thread CTAs held to 160 registers: the searches and E-steps of the other registrations in flight
+                                    // run beside a solve on its SMs (tools/sweep.py, 32 pairs: 399 -> 423 registrations/s; 176 / 144 registers: 420)
 constexpr int kBatchLmGrid = 37;
 constexpr int kLoneCtlShare8 = 8, kBatchCtlShare8 = 8;  // sweep share of the LM controller block (eighths)
 // Pairing (SICP_PAIR=1): registrations of a batch run in pairs that share one LM launch per pass, whose blocks alternate
@@ -435,10 +436,10 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     SICP_CUDA(cudaEventRecord(fork, base));
   }
   const int kChunk = std::max(1, env_int("SICP_CHUNK", 3));  // pass-by-pass path: passes enqueued between two readbacks
-  // LM kernel shape.  A lone solve takes every SM (shape 0, one 256-thread CTA each).  Concurrent solves use a shape
-  // that leaves registers free on its SMs and a grid of a fraction of the machine: their sweeps are longer, so the
-  // latency-bound control step between sweeps idles a smaller share of the SMs, and the kNN / covariance kernels of
-  // the other registrations in flight share those SMs.
+  // LM kernel shape.  A lone solve takes every SM (shape 0, one 256-thread CTA each at ~240 registers).  Concurrent solves
+  // use the register-capped shape and a grid of a quarter of the machine: their sweeps are longer, so the latency-bound
+  // control step between sweeps idles a smaller share of the SMs, and the kNN / covariance / E-step kernels of the other
+  // registrations in flight fit beside an LM CTA on the same SM (it leaves 24k registers and 55 KB of shared memory).
   const int variant = lone ? 0 : std::min(std::max(env_int("SICP_LM_VARIANT", kBatchLmVariant), 0), kLmVariants - 1);
   sicp_status rc = SICP_OK;
   std::vector<int> slot_job(NS, -1);
