@@ -161,8 +161,11 @@ struct Moments {
   }
 };
 
+#ifndef SICP_COV_MINB
+#define SICP_COV_MINB 1   // resident CTAs per SM the register allocation is held to (1: no cap, 88 registers at k = 20)
+#endif
 template <int K>
-__global__ void __launch_bounds__(kThreads) self_knn_pca_kernel(CloudView cv, const int* __restrict__ slot_of_orig, int k, double* __restrict__ nrm,
+__global__ void __launch_bounds__(kThreads, SICP_COV_MINB) self_knn_pca_kernel(CloudView cv, const int* __restrict__ slot_of_orig, int k, double* __restrict__ nrm,
                                                                 int* __restrict__ selfnn, uint8_t* __restrict__ nbr_label) {
   __shared__ WarpScratch s_ws[kWarpsPerBlock];
   __shared__ Segment s_seg[kWarpsPerBlock];
