@@ -1,7 +1,8 @@
 """Batch / lone throughput sweep over the library's tuning knobs (environment variables read per call).
 
   python tools/sweep.py B "VARIANT:GRID:CONC[:GRAPH[:REUSE]],..." [reps]      e.g.  16 "0:37:8,1:74:8:0,2:74:12:1:1"
-  VARIANT = LM kernel shape (SICP_LM_VARIANT), GRID = CTAs of a batch solve (SICP_LM_GRID), CONC = registrations in flight,
+  VARIANT = LM kernel shape (SICP_LM_VARIANT: 0 full registers, 1 128-thread CTAs, 2/3/4 = 176/160/144 registers), GRID = CTAs of a batch solve
+  (SICP_LM_GRID), CONC = registrations in flight,
   GRAPH = device-resident outer loop on/off (SICP_GRAPH), REUSE = graph exec updated in place (SICP_GRAPH_REUSE).
 Prints registrations/s (best and median of `reps` batches; clouds are created from host arrays inside the timed span, like
 the e2e leg of bench.py) and, first, the wall time of one lone registration.
