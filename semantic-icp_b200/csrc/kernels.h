@@ -63,6 +63,7 @@ sicp_status launch_estep(const sicp_cloud* src, const sicp_cloud* tgt, const LMC
 // M-step: one inner solve (ceres::Solve at impl/gicp.hpp:149-151) + outer-loop bookkeeping, cooperative kernel
 int lm_grid_blocks(int device);
 int lm_max_grid(int device, int algo, int variant);
+sicp_status precompute_cloud(sicp_cloud* c, int k_cov, double eps, int n_classes, const double* cm, bool defer_label_check);  // knn_cov.cu
 // cond_handle != 0: the launch is being captured as the last node of a graph WHILE body; the kernel sets the handle to
 // "not converged" so that the graph runs another pass without the host
 sicp_status launch_lm(const sicp_cloud* src, const LMConfig& cfg, const char* d_rec, RegCtl* d_ctl,

@@ -404,6 +404,17 @@ sicp_status sicp_debug_warp_trace(unsigned* out, int n) {
 }
 
 sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, const double* cm) {
+  return sicp::precompute_cloud(c, k_cov, eps, N, cm, false);
+}
+
+}  // extern "C"
+
+// defer_label_check: the label range of a cloud created from DEVICE labels is only known on the device (computed by its
+// build).  Fetching it here costs a host synchronisation per cloud on the registration's stream; the batch executor
+// instead reads the two words back with the registration's control block and validates them when the registration
+// completes (register.cu: Job::check_labels).  The kernels are safe either way (label_vector_kernel ignores labels
+// outside 1..N).
+sicp_status sicp::precompute_cloud(sicp_cloud* c, int k_cov, double eps, int N, const double* cm, bool defer_label_check) {
   SICP_REQUIRE(c, "cloud is null");
   SICP_REQUIRE(k_cov >= 1 && k_cov <= kMaxK, "k_cov must be in 1..32");
   SICP_REQUIRE(N >= 0 && N <= kMaxClasses, "n_classes must be in 0..64");
@@ -429,14 +440,16 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
   uint8_t* d_nbr = nullptr;
   double* d_cm = nullptr;
   if (N > 0) {
-    if (!c->label_range_known && c->nslots) {  // device-resident labels: fetch the range computed at build time
+    if (!c->label_range_known && c->nslots && !defer_label_check) {  // device-resident labels: fetch the range computed at build time
       unsigned h_mm[2];
       SICP_CUDA(cudaMemcpyAsync(h_mm, c->d_bb + 6, 8, cudaMemcpyDeviceToHost, st));
       SICP_CUDA(cudaStreamSynchronize(st));
       c->min_label = h_mm[0]; c->max_label = h_mm[1]; c->label_range_known = true;
     }
-    SICP_REQUIRE(c->nslots == 0 || c->min_label >= 1, "label 0 found: EM-ICP labels must be 1..N");  // em_icp.hpp:301 indexes label-1
-    SICP_REQUIRE(c->nslots == 0 || (int)c->max_label <= N, "label exceeds n_classes: EM-ICP labels must be 1..N");
+    if (c->label_range_known) {
+      SICP_REQUIRE(c->nslots == 0 || c->min_label >= 1, "label 0 found: EM-ICP labels must be 1..N");  // em_icp.hpp:301 indexes label-1
+      SICP_REQUIRE(c->nslots == 0 || (int)c->max_label <= N, "label exceeds n_classes: EM-ICP labels must be 1..N");
+    }
     SICP_CUDA(cudaMallocAsync(&d_nbr, (size_t)kMaxK * std::max(1, c->nslots), st));
     SICP_CUDA(cudaMallocAsync(&c->d_avec, sizeof(double) * N * std::max(1, c->nslots), st));
     SICP_CUDA(cudaMallocAsync(&d_cm, sizeof(double) * N * N, st));
@@ -465,6 +478,8 @@ sicp_status sicp_cloud_precompute(sicp_cloud* c, int k_cov, double eps, int N, c
   c->pre_valid = true;
   return SICP_OK;
 }
+
+extern "C" {
 
 static sicp_status download_rows(const sicp_cloud* c, const double* d_in, int cols, int soa, double* out) {
   cudaStream_t st = current_stream();

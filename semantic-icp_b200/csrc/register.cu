@@ -95,7 +95,8 @@ sicp_status validate_pose7(const double* p7, const char* what, bool nullable) {
 // a single wave with a long tail (a few slow warps), so for a LONE registration the target runs on a helper stream
 // beside the source on `st`; `st` then waits for both ready events.  In a batch (helper == nullptr) both run on `st`:
 // the tails are already filled by the other registrations in flight.
-static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* o, cudaStream_t st, cudaStream_t helper) {
+static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, const sicp_options* o, cudaStream_t st, cudaStream_t helper,
+                                   bool defer_label_check = false) {
   const int N = algo == SICP_ALGO_EM ? o->n_classes : 0;
   cudaStream_t saved = current_stream();
   sicp_status rc = SICP_OK;
@@ -103,11 +104,11 @@ static sicp_status precompute_pair(int algo, sicp_cloud* src, sicp_cloud* tgt, c
     bool cached;
     { std::lock_guard<std::mutex> lk(tgt->mu); cached = tgt->pre_valid; }
     sicp_set_stream(helper && !cached ? helper : st);
-    rc = sicp_cloud_precompute(tgt, o->k_cov, o->epsilon, N, o->confusion);
+    rc = precompute_cloud(tgt, o->k_cov, o->epsilon, N, o->confusion, defer_label_check);
   }
   if (rc == SICP_OK) {
     sicp_set_stream(st);
-    rc = sicp_cloud_precompute(src, o->k_cov, o->epsilon, N, o->confusion);
+    rc = precompute_cloud(src, o->k_cov, o->epsilon, N, o->confusion, defer_label_check);
   }
   sicp_set_stream(saved);
   SICP_CHECK(rc);
@@ -148,7 +149,7 @@ struct Slot {
   char* d_rec = nullptr;         // record group blocks of the current pass (kernels.h: struct Rec), sized for k_c = 4
   RegCtl* d_ctl = nullptr; double* d_partials = nullptr; int* d_map = nullptr;
   RegCtl* h_ctl = nullptr;        // pinned
-  int* h_map = nullptr;           // pinned, kMaxSegMap ints (class map staging)
+  int* h_map = nullptr;           // pinned, kMaxSegMap ints (class map staging) + 4 words: label ranges of the pair's clouds
   cudaGraphExec_t exec = nullptr;       // WHILE { kNN, E-step, LM } of one registration
   cudaGraphExec_t exec_pair = nullptr;  // ... of a pair of registrations (two kNN + E-step chains, one paired LM launch)
   SlotNote note{nullptr, 0};
@@ -165,7 +166,7 @@ struct Slot {
       SICP_CUDA(cudaMemset(d_partials, 0, sizeof(double) * kLmPartialsDoubles));  // LMSync starts at zero; generations continue from there
       SICP_CUDA(cudaMalloc(&d_map, sizeof(int) * kMaxSegMap));
       SICP_CUDA(cudaMallocHost(&h_ctl, sizeof(RegCtl)));
-      SICP_CUDA(cudaMallocHost(&h_map, sizeof(int) * kMaxSegMap));
+      SICP_CUDA(cudaMallocHost(&h_map, sizeof(int) * (kMaxSegMap + 4)));
     }
     nc = std::max<size_t>(nc, 1);
     if (nc > cap_nc) {
@@ -294,6 +295,36 @@ struct Job {
     return SICP_OK;
   }
   const int* class_map() const { return cfg.algo == SICP_ALGO_SEMANTIC ? sl->d_map : nullptr; }
+  // EM labels must be 1..N (em_icp.hpp:301).  For clouds created from device labels the range is only known on the device:
+  // it is read back with the registration (no host synchronisation before the passes) and checked when the job completes.
+  bool labels_pending = false;
+  sicp_status fetch_label_ranges() {
+    if (algo != SICP_ALGO_EM) return SICP_OK;
+    unsigned* h = reinterpret_cast<unsigned*>(sl->h_map + Slot::kMaxSegMap);
+    const sicp_cloud* cl[2] = {src, tgt};
+    for (int i = 0; i < 2; i++) {
+      bool known;
+      { std::lock_guard<std::mutex> lk(const_cast<sicp_cloud*>(cl[i])->mu); known = cl[i]->label_range_known || cl[i]->nslots == 0; }
+      h[2 * i] = 1; h[2 * i + 1] = 1;  // "in range" unless the device says otherwise
+      if (known) continue;
+      SICP_CUDA(cudaMemcpyAsync(h + 2 * i, cl[i]->d_bb + 6, 8, cudaMemcpyDeviceToHost, st));
+      labels_pending = true;
+    }
+    return SICP_OK;
+  }
+  sicp_status check_labels() {
+    if (!labels_pending) return SICP_OK;
+    const unsigned* h = reinterpret_cast<const unsigned*>(sl->h_map + Slot::kMaxSegMap);
+    sicp_cloud* cl[2] = {src, tgt};
+    for (int i = 0; i < 2; i++) {
+      if (cl[i]->nslots == 0) continue;
+      { std::lock_guard<std::mutex> lk(cl[i]->mu);
+        if (!cl[i]->label_range_known) { cl[i]->min_label = h[2 * i]; cl[i]->max_label = h[2 * i + 1]; cl[i]->label_range_known = true; } }
+      SICP_REQUIRE(cl[i]->min_label >= 1, "label 0 found: EM-ICP labels must be 1..N");
+      SICP_REQUIRE((int)cl[i]->max_label <= opts->n_classes, "label exceeds n_classes: EM-ICP labels must be 1..N");
+    }
+    return SICP_OK;
+  }
   // correspondences + E-step of one outer pass on stream `s`
   sicp_status enqueue_corr(cudaStream_t s) {
     const int* stop = &sl->d_ctl->converged;
@@ -460,9 +491,10 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     SICP_CHECK(ensure_built(jb.src, st));
     SICP_CHECK(ensure_built(jb.tgt, st));
     jb.tm.begin(SICP_STAGE_COV, st);
-    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, st, lone ? t_helper.st : nullptr);
+    const sicp_status r = precompute_pair(jb.algo, jb.src, jb.tgt, jb.opts, st, lone ? t_helper.st : nullptr, true);
     jb.tm.end(st);
     SICP_CHECK(r);
+    SICP_CHECK(jb.fetch_label_ranges());
     return jb.start(init7s + 7 * (size_t)j);
   };
   auto launch = [&](int slot) -> sicp_status {
@@ -507,9 +539,11 @@ static sicp_status run_jobs(std::vector<Job>& jobs, const double* init7s, int ma
     if (jobs[j].complete()) {
       jobs[j].finish();
       if (jobs[j].partner) jobs[j].partner->finish();
+      rc = jobs[j].check_labels();
+      if (rc == SICP_OK && jobs[j].partner) rc = jobs[j].partner->check_labels();
       live--;
       slot_job[s] = -1;
-      if (next < nj) rc = launch(s);
+      if (rc == SICP_OK && next < nj) rc = launch(s);
     } else {
       rc = jobs[j].advance(kChunk);
     }

@@ -440,3 +440,40 @@ def test_class_partition_on_device(sicp, oracle, room):
     for nclass in (129, 700):                                       # over the class limit / over the table size
         with pytest.raises(sicp.SicpError, match="at most 128"):
             sicp.Cloud(xyz, (np.arange(3000) % nclass).astype(np.uint32) * 977, layout=sicp.CLOUD_PER_CLASS)
+
+
+def test_device_label_ranges_are_checked_when_the_registration_completes(sicp, pkg, room):
+    """Clouds created from DEVICE labels: the 1..N check of EM-ICP (em_icp.hpp:301 indexes label - 1) reads the range back
+    with the registration instead of synchronising before it; results equal those of host-created clouds, bad labels still
+    fail (lone and batch), and a direct precompute call keeps the immediate check."""
+    import torch
+
+    p = room
+    opts = sicp.default_options(sicp.ALGO_EM, cm=p["cm"])
+    n = len(p["src_xyz"])
+
+    def dev_cloud(xyz, lab):
+        dx = torch.from_numpy(np.ascontiguousarray(xyz)).cuda()
+        dl = torch.from_numpy(np.ascontiguousarray(lab).astype(np.int32)).cuda()
+        torch.cuda.synchronize()
+        return sicp.Cloud.from_device(dx.data_ptr(), dl.data_ptr(), len(xyz)), (dx, dl)
+
+    s, keep_s = dev_cloud(p["src_xyz"], p["src_labels"])
+    t, keep_t = dev_cloud(p["tgt_xyz"], p["tgt_labels"])
+    ref = sicp.register(sicp.ALGO_EM, sicp.Cloud(p["src_xyz"], p["src_labels"]), sicp.Cloud(p["tgt_xyz"], p["tgt_labels"]), opts, p["init"])
+    got = sicp.register(sicp.ALGO_EM, s, t, opts, p["init"])
+    assert np.array_equal(got["pose"], ref["pose"]) and got["outer_iter"] == ref["outer_iter"]
+    for bad_value in (0, p["N"] + 1):
+        lab = p["src_labels"].copy()
+        lab[n // 2] = bad_value
+        b, keep_b = dev_cloud(p["src_xyz"], lab)
+        with pytest.raises(sicp.SicpError, match="1..N"):
+            sicp.register(sicp.ALGO_EM, b, t, opts, p["init"])
+        b2, keep_b2 = dev_cloud(p["src_xyz"], lab)
+        with pytest.raises(sicp.SicpError, match="1..N"):
+            sicp.register_batch(sicp.ALGO_EM, [s, b2, s], [t, t, t], opts, np.stack([p["init"]] * 3))
+        b3, keep_b3 = dev_cloud(p["src_xyz"], lab)
+        with pytest.raises(sicp.SicpError, match="1..N"):
+            b3.precompute(20, 1e-3, p["cm"])
+    again = sicp.register(sicp.ALGO_EM, s, t, opts, p["init"])  # the library is usable after a failed batch
+    assert np.array_equal(again["pose"], ref["pose"])
