@@ -113,8 +113,9 @@ uint64_t sicp_launch_count(void);
  * (12 packed, 16 pcl::PointXYZ, 32 pcl::PointXYZL).  labels may be NULL (GICP).  At most 2^26 points.           */
 sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* labels, size_t label_stride, size_t n,
                               int layout, int device, sicp_cloud** out);
-/* Same, inputs already resident in HBM: d_xyz is packed n*3 float32, d_labels n uint32 (or NULL).  The EM label-range
- * check (labels in 1..n_classes) of such a cloud is made when a registration using it completes, not before it starts. */
+/* Same, inputs already resident in HBM: d_xyz is packed n*3 float32, d_labels n uint32 (or NULL).
+ * For both kinds of cloud the EM label-range check (labels in 1..n_classes) uses the range computed by the device build: a
+ * registration reports a violation when it completes, sicp_cloud_precompute reports it at once. */
 sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_labels, size_t n, int layout, int device,
                                      sicp_cloud** out);
 void sicp_cloud_destroy(sicp_cloud* cloud);

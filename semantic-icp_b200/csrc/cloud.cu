@@ -400,20 +400,10 @@ static sicp_status create_common(float* d_xyz, uint32_t* d_labels, const void* h
   sicp_status rc = SICP_OK;
   if (layout == SICP_CLOUD_PER_CLASS) rc = classify_device(c, d_labels, n, &d_rank, &sizes, st);
   else sizes.push_back((int)n);
-  if (rc == SICP_OK && h_labels && n) {  // host-side label range (labels must be 1..N for EM, em_icp.hpp:301)
-    // eight independent accumulators: the scan is on the host's critical path of every cloud creation (a 120k-point cloud
-    // took ~0.1 ms with one dependent min/max chain — 10 ms per 48-pair step of the e2e path)
-    uint32_t lo8[8], hi8[8];
-    for (int k = 0; k < 8; k++) { lo8[k] = 0xffffffffu; hi8[k] = 0; }
-    const char* base = static_cast<const char*>(h_labels);
-    size_t i = 0;
-    for (; i + 8 <= n; i += 8)
-      for (int k = 0; k < 8; k++) { uint32_t l; std::memcpy(&l, base + (i + k) * label_stride, 4); lo8[k] = std::min(lo8[k], l); hi8[k] = std::max(hi8[k], l); }
-    for (; i < n; i++) { uint32_t l; std::memcpy(&l, base + i * label_stride, 4); lo8[0] = std::min(lo8[0], l); hi8[0] = std::max(hi8[0], l); }
-    uint32_t lo = lo8[0], hi = hi8[0];
-    for (int k = 1; k < 8; k++) { lo = std::min(lo, lo8[k]); hi = std::max(hi, hi8[k]); }
-    c->min_label = lo; c->max_label = hi; c->label_range_known = true;
-  }
+  // The label range (EM-ICP needs labels in 1..N, em_icp.hpp:301) is computed on the device by the build for host- and
+  // device-created clouds alike and validated by whoever needs it (knn_cov.cu: precompute_cloud; register.cu:
+  // Job::check_labels); a host-side scan here cost 20-80 us per 120k-point cloud on the caller's thread.
+  (void)h_labels; (void)label_stride;
   if (rc == SICP_OK) layout_cloud(c, sizes);
   static const bool eager = [] { const char* e = getenv("SICP_EAGER_BUILD"); return e && *e && *e != '0'; }();
   if (rc == SICP_OK && cudaEventCreateWithFlags(&c->built_ev, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = SICP_ERR_CUDA; }
