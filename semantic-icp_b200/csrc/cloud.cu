@@ -387,11 +387,9 @@ sicp_status sicp_device_count(int* count) {
 uint64_t sicp_launch_count(void) { return g_launches; }
 sicp_status sicp_set_stream(void* s) { g_stream = (cudaStream_t)s; return SICP_OK; }
 
-// h_labels (nullable) are the caller's labels, label_stride bytes apart, when they live on the host.
 // d_xyz / d_labels are staging buffers OWNED by this call (allocated stream-ordered on the current stream): they are
 // freed after an eager build, or kept by the cloud until its deferred build.
-static sicp_status create_common(float* d_xyz, uint32_t* d_labels, const void* h_labels, size_t label_stride, size_t n, int layout,
-                                 int device, sicp_cloud** out) {
+static sicp_status create_common(float* d_xyz, uint32_t* d_labels, size_t n, int layout, int device, sicp_cloud** out) {
   cudaStream_t st = current_stream();
   sicp_cloud* c = new sicp_cloud();
   c->device = device; c->layout = layout; c->n = n; c->has_labels = d_labels != nullptr;
@@ -403,7 +401,6 @@ static sicp_status create_common(float* d_xyz, uint32_t* d_labels, const void* h
   // The label range (EM-ICP needs labels in 1..N, em_icp.hpp:301) is computed on the device by the build for host- and
   // device-created clouds alike and validated by whoever needs it (knn_cov.cu: precompute_cloud; register.cu:
   // Job::check_labels); a host-side scan here cost 20-80 us per 120k-point cloud on the caller's thread.
-  (void)h_labels; (void)label_stride;
   if (rc == SICP_OK) layout_cloud(c, sizes);
   static const bool eager = [] { const char* e = getenv("SICP_EAGER_BUILD"); return e && *e && *e != '0'; }();
   if (rc == SICP_OK && cudaEventCreateWithFlags(&c->built_ev, cudaEventDisableTiming) != cudaSuccess) { set_error("event creation failed"); rc = SICP_ERR_CUDA; }
@@ -477,7 +474,7 @@ sicp_status sicp_cloud_create(const void* xyz, size_t xyz_stride, const void* la
       else SICP_CUDA(cudaMemcpy2DAsync(d_lab, 4, labels, label_stride, 4, n, cudaMemcpyHostToDevice, st));
     }
   }
-  return create_common(d_xyz, d_lab, labels, label_stride, n, layout, device, out);  // takes the staging buffers over
+  return create_common(d_xyz, d_lab, n, layout, device, out);  // takes the staging buffers over
 }
 
 sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_labels, size_t n, int layout, int device, sicp_cloud** out) {
@@ -496,7 +493,7 @@ sicp_status sicp_cloud_create_device(const float* d_xyz, const uint32_t* d_label
     SICP_CUDA(cudaMallocAsync(&s_lab, std::max<size_t>(1, n) * 4, st));
     if (n) SICP_CUDA(cudaMemcpyAsync(s_lab, d_labels, 4 * n, cudaMemcpyDeviceToDevice, st));
   }
-  return create_common(s_xyz, s_lab, nullptr, 4, n, layout, device, out);
+  return create_common(s_xyz, s_lab, n, layout, device, out);
 }
 
 void sicp_cloud_destroy(sicp_cloud* c) {
